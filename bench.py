@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- Mcell-RHS evaluations/s of the Runge-Kutta-Merson + phase-field/heat RHS hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N=1; N>1 under torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    (the reference's CPU code on the host cores)
+
+A "step" is one Merson step ATTEMPT over the whole grid (5 right-hand-side evaluations in the
+reference; 4 + the K1 evaluations actually needed here).  The workload is an
+archived case of the reference (default: the "400" high-resolution case, 200x200x400 nodes,
+calc_mode 1) or a synthetic sphere-pack cube; see --workload.
+
+Prints ONE JSON line (rank 0).  `value` times the device-resident path, `e2e` the same K
+attempts through upload -> solve -> download with pinned HOST buffers, `roofline` the dominant
+stage kernel against the measured HBM peak, `cpu_baseline` the reference CPU code on this host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from porousfreezethaw_b200 import cases  # noqa: E402
+
+# algorithmic HBM bytes per cell of each fused stage kernel:
+# float64, u and p evolve (16 B per array pair), gl static (8 B), one sweep per stage
+STAGE_BYTES_HEAT = [40, 56, 40, 72, 88]      # sum 296 B per attempt = 59.2 B per cell-RHS
+STAGE_BYTES_NOHEAT = [24, 32, 24, 40, 48]    # calc_mode 10/11: only p evolves; u, gl static reads
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_spec(name: str, nranks: int):
+    if name.startswith("cube-"):
+        # cube-400 | cube-800 (strong scaling) | cube-800w (weak: 800x800x(100*N))
+        tag = name[5:]
+        if tag.endswith("w"):
+            n = int(tag[:-1])
+            spec = cases.cube_case(n, nz=100 * nranks)
+            scaling = "weak"
+        else:
+            n = int(tag)
+            spec = cases.cube_case(n)
+            scaling = "strong"
+        return spec, scaling, "synthetic sphere pack (numpy default_rng(20251018), 4000 spheres)"
+    spec = cases.archived_case(name)
+    sph = os.path.join(ROOT, "oracle", "_ref", "data", "spheres_positions.txt")
+    if os.path.exists(sph):
+        spec.spheres = np.loadtxt(sph).reshape(-1, 3)
+        geo = "reference sphere pack (data/spheres_positions.txt, 200 spheres)"
+    else:
+        s = cases.synthetic_spheres(200, zmax=1.6)
+        spec.spheres = s
+        geo = "synthetic sphere pack (200 spheres; the reference's data file is not in this tree)"
+    return spec, "strong", geo
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons, pw = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# the reference CPU path (oracle/_ref when the reference was compiled in the container,
+# else our restatement oracle/pft_oracle.c) -- used by cpu_baseline and by --impl reference
+
+def cpu_reference_run(spec, warmup: int, steps: int):
+    """Times `steps` Merson attempts of the reference's own CPU implementation (after `warmup`
+    attempts) with all host threads.  Returns (Mcell-RHS/s, dict describing the run)."""
+    from oracle import pyoracle as po
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ.setdefault("OMP_SCHEDULE", "static")      # apps/intertrack-hybrid-S-freezing/Run:13-19
+    os.environ.setdefault("OMP_PROC_BIND", "false")
+    po.build("oracle")
+    case = po.Case(spec.n1, spec.n2, spec.n3, spec.L1, spec.L2, spec.L3, spec.param_array(), spec.calc_mode)
+    u, p, gl = spec.initial_fields()
+    orc = po.Oracle(case)
+    w = case.pack(u, p, gl)
+    orc.rasterise(spec.spheres, w)            # OpenMP rasteriser of the restatement (bit-identical to the reference's)
+    if po.have_ref():
+        kind = "reference"
+        ref = po.Reference()
+        gl_r = case.interior(w)[2]
+        ref.setup(case, u, p, gl_r, None, t0=0.0, tau=spec.tau, tau_min=spec.tau_min, delta=spec.delta, use_callback=True)
+        del w
+
+        def run_attempts(n):
+            t0_, _, _, tot0 = ref.state()
+            ref.lib.pftref_break_after(tot0 + n)
+            t = time.perf_counter()
+            ref.solve(spec.final_time)
+            dt = time.perf_counter() - t
+            return ref.state()[3] - tot0, dt
+    else:
+        kind = "port"
+        s = orc.new_system(t=0.0, h=spec.tau, h_min=spec.tau_min, delta=spec.delta)
+        work = np.zeros(5 * w.size)
+
+        def run_attempts(n):
+            tot0 = s.steps_total
+            s.max_attempts = n
+            t = time.perf_counter()
+            orc.solve(s, w, spec.final_time, work)
+            dt = time.perf_counter() - t
+            return s.steps_total - tot0, dt
+    if warmup > 0:
+        run_attempts(warmup)
+    n, dt = run_attempts(steps)
+    value = spec.cells * 5.0 * n / dt / 1e6
+    info = {"value": value, "unit": "Mcell-RHS/s", "cores": int(os.environ["OMP_NUM_THREADS"]), "kind": kind,
+            "sample": f"{n} Merson attempts (5 RHS each) of {spec.name} {spec.n1}x{spec.n2}x{spec.n3} after {warmup} warm-up attempts, "
+                      f"reference flags -O1 -fopenmp, {dt:.2f} s"}
+    return value, n, dt, info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    spec, scaling, geo = make_spec(args.workload, max(1, args.gpus))
+    value, n, dt, info = cpu_reference_run(spec, args.warmup, args.steps)
+    line = {
+        "impl": "reference", "metric": "Mcell-RHS evals/s", "value": value, "unit": "Mcell-RHS/s",
+        "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(n, 1),
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": spec.name, "grid": [spec.n1, spec.n2, spec.n3], "calc_mode": spec.calc_mode, "geometry": geo,
+                   "mode": "adaptive"},
+        "cpu_baseline": info,
+        "e2e": {"value": value, "unit": "Mcell-RHS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default=os.environ.get("PFT_BENCH_WORKLOAD", "400-SigmaP1-P-smallsigma"))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--profile-steps", type=int, default=40)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from porousfreezethaw_b200.solver import SlabSolver
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; porousfreezethaw_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    N = world
+
+    spec, scaling, geo = make_spec(args.workload, N)
+    sol = SlabSolver(spec, rank=rank, nranks=N, device=local)
+    if N > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(sol.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        sol.comm_init(bytes(uid.cpu().numpy().tobytes()))
+
+    # initial condition of this rank's slab, sphere pack rasterised on the device
+    u, p, gl = spec.initial_fields(first_row=sol.first_row, n3_local=sol.n3)
+    sol.upload_interior(u, p, gl)
+    sol.rasterise(spec.spheres)
+    del u, p, gl
+
+    def barrier():
+        torch.cuda.synchronize()
+        if N > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def allmax(x: float) -> float:
+        if N == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x: float) -> float:
+        if N == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    T_END = spec.final_time
+
+    # ---- warm-up, then EXACTLY K attempts, device-resident --------------------------------
+    sol.solve(T_END, max_attempts=args.warmup)
+    st0 = sol.stats()
+    ev0 = sol.sys.rhs_evals
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall = time.perf_counter()
+    r = sol.solve(T_END, max_attempts=args.steps)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if sampler else None
+    st1 = sol.stats()
+    dev_ms = allmax(st1["device_ms_total"])                 # CUDA events on the solver's own stream, max over ranks
+    attempts = st1["attempts"] - st0["attempts"]
+    rhs = sol.sys.rhs_evals - ev0
+    total_cells = allsum(float(sol.cells))
+    value = total_cells * rhs / (dev_ms * 1e-3) / 1e6
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+    stage_launches = [a - b for a, b in zip(st1["stage_launches"], st0["stage_launches"])]
+
+    # ---- per-stage device times (CUDA events around every stage kernel on its stream) ----
+    os.environ["PFT_PROFILE_STAGES"] = "1"
+    # (a second solver object: the profiling switch is read when a solver is created)
+    u_, p_, gl_ = sol.download_interior()
+    solp = SlabSolver(spec, rank=rank, nranks=N, device=local)
+    if N > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(solp.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        solp.comm_init(bytes(uid.cpu().numpy().tobytes()))
+    solp.upload_interior(u_, p_, gl_)
+    solp.sys.t, solp.sys.h = sol.sys.t, sol.sys.h
+    del u_, p_, gl_
+    solp.solve(T_END, max_attempts=3)
+    solp.reset_stats()
+    barrier()
+    solp.solve(T_END, max_attempts=args.profile_steps)
+    barrier()
+    stp = solp.stats()
+    del os.environ["PFT_PROFILE_STAGES"]
+    sb = STAGE_BYTES_HEAT if spec.calc_mode in (0, 1, 2) else STAGE_BYTES_NOHEAT
+    peak, peak_src = peaks()
+    stages = []
+    for i in range(5):
+        nl = stp["stage_launches"][i]
+        if nl == 0:
+            continue
+        ms = stp["stage_ms"][i] / nl
+        gbs = sol.cells * sb[i] / (ms * 1e-3) / 1e9
+        stages.append({"stage": i + 1, "launches": nl, "avg_ms": ms, "bytes_per_cell": sb[i], "achieved_gbs": gbs, "frac": gbs / peak})
+    dom = max(stages, key=lambda s: s["avg_ms"] * s["launches"])
+    roofline = {"bound": "hbm", "kernel": f"merson_stage<{dom['stage']}>", "achieved": dom["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": sol.cells * dom["bytes_per_cell"], "avg_launch_ms": dom["avg_ms"],
+                "per_stage": stages}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tr):
+        try:
+            with open(tr) as f:
+                tj = json.load(f)
+            key = f"{spec.name}:stage{dom['stage']}"
+            if key in tj:
+                roofline["traffic"] = tj[key]
+        except Exception:
+            pass
+    solp.close()
+
+    # ---- end to end: pinned HOST buffers -> upload -> K attempts -> download ---------------
+    xh = torch.empty(3 * sol.SIZE, dtype=torch.float64, pin_memory=True).numpy()
+    sol.download(xh)                                         # a valid padded host image of the current state
+    barrier()
+    ev0 = sol.sys.rhs_evals
+    a0 = sol.sys.steps_total
+    t0 = time.perf_counter()
+    sol.upload(xh)
+    sol.solve(T_END, max_attempts=args.steps)
+    sol.download(xh)
+    barrier()
+    e2e_s = allmax(time.perf_counter() - t0)
+    e2e_attempts = sol.sys.steps_total - a0
+    e2e_value = total_cells * (sol.sys.rhs_evals - ev0) / e2e_s / 1e6
+    nbytes = 3 * sol.SIZE * 8
+    e2e = {"value": e2e_value, "unit": "Mcell-RHS/s", "h2d_bytes_per_step": nbytes / max(e2e_attempts, 1),
+           "d2h_bytes_per_step": nbytes / max(e2e_attempts, 1), "attempts": e2e_attempts,
+           "note": "one solve call = upload(x) + K attempts + download(x), as RK_MPI_SA_solve with a host-resident x"}
+
+    # ---- the reference CPU path on this host (rank 0, N == 1 only) ------------------------
+    cpu = None
+    if rank == 0 and N == 1 and not args.no_cpu_baseline:
+        try:
+            _, _, _, cpu = cpu_reference_run(spec, 1, args.cpu_steps)
+        except Exception as e:      # the baseline is reported, never fatal
+            cpu = {"value": None, "unit": "Mcell-RHS/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
+
+    if rank == 0:
+        st = sol.stats()
+        line = {
+            "metric": "Mcell-RHS evals/s", "value": value, "unit": "Mcell-RHS/s", "n_gpus": N,
+            "steps": attempts, "warmup": args.warmup, "ms_per_step": dev_ms / max(attempts, 1),
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": spec.name, "grid": [spec.n1, spec.n2, spec.n3], "calc_mode": spec.calc_mode,
+                       "geometry": geo, "mode": "adaptive (delta 1e-3)", "cache": "inputs larger than L2 (no flush needed)"
+                       if sol.cells * 13 * 8 > 2 * 126e6 else "working set fits L2",
+                       "parallelism": f"z-slabs x{N}", "tile": [st["tile_x"], st["tile_y"]], "z_chunk": st["z_chunk"],
+                       "rhs_evals_per_attempt": rhs / max(attempts, 1),
+                       "accepted": st1["accepted"] - st0["accepted"]},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "wall_ms_per_step": 1e3 * t_wall / max(attempts, 1),
+            "roofline_step": {"achieved": total_cells / N * sum(b * n for b, n in zip(sb, stage_launches)) / (dev_ms * 1e-3) / 1e9,
+                              "peak": peak, "unit": "GB/s",
+                              "frac": total_cells / N * sum(b * n for b, n in zip(sb, stage_launches)) / (dev_ms * 1e-3) / 1e9 / peak,
+                              "note": "algorithmic bytes of every stage kernel launched in the timed region / device time, per GPU (includes launch gaps and host round trips)"},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    sol.close()
+    if N > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

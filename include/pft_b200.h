@@ -1,0 +1,148 @@
+/*
+ * pft_b200.h -- C ABI of libpft_b200.so: the B200-native (sm_100a, float64) implementation of
+ * PorousFreezeThaw's hot path, i.e. the Runge-Kutta-Merson adaptive integrator driving the
+ * phase-field / heat right-hand side on a z-slab of the grid that lives in this GPU's HBM.
+ *
+ * Plain C, no torch / C++ types.  Every entry point returns 0 on success or a negative
+ * PFT_E* code (pft_last_error() gives the text); nothing throws across the boundary.  All
+ * host pointers are caller-owned.  One pft_solver is driven by one host thread.
+ *
+ * There is NO CPU fallback: pft_create fails with PFT_ENODEVICE when no CUDA device is usable.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference root):
+ *
+ *   pft_create / pft_destroy   RK_MPI_SA_init / RK_MPI_SA_cleanup (scratch K1,K3,K4,K5,aux:
+ *                              modules/RK_MPI_SAsolver_hybrid2/RK_MPI_SAsolver_hybrid2.c:72-136)
+ *                              + the block geometry of apps/intertrack-hybrid-S-freezing/
+ *                              intertrack.c:1776-1800 + the derived constants of
+ *                              equation.c:442-447,605-612
+ *   pft_upload / pft_download  the in-place host array `system->x` of RK_MPI_S_SOLUTION
+ *                              (include/RK_MPI_SAsolver.h:196-289) in the padded layout of
+ *                              intertrack.c:431,2149-2156
+ *   pft_rhs_host               RK_RightHandSide f(t, w, dw) = f_generic_model01 / f_generic_model2
+ *                              (equation.c:566-741, :745-884) incl. bcond_setup (:266-284)
+ *   pft_solve                  RK_MPI_SA_solve (RK_MPI_SAsolver_hybrid2.c:215-770; twin
+ *                              modules/RK_MPI_SAsolver_hybrid/RK_MPI_SAsolver_hybrid.c)
+ *   pft_comm_*                 the z-halo exchange sync_solution (equation.c:290-326) and
+ *                              MPI_Allreduce(MAX) (RK_MPI_SAsolver_hybrid2.c:572)
+ *   pft_rasterise              the sphere rasteriser of PrecalculateData (equation.c:474-529)
+ *   pft_ice_fraction           scripts/avg.sh:9-20 (mean(p > 0.5))
+ */
+#ifndef PFT_B200_H
+#define PFT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFT_NPARAM 30            /* apps/intertrack-hybrid-S-freezing/model.c:44-59 */
+#define PFT_NVAR   3             /* u, p, gl -- model.c:32-40 */
+#define PFT_BT     2             /* bcond_thickness of the HOST layout, equation.c:38 */
+
+/* error codes (pft_solve additionally returns the reference's own 0 / 1 / -2 / -4 codes) */
+#define PFT_OK           0
+#define PFT_EINVAL     (-22)
+#define PFT_ENOMEM     (-12)
+#define PFT_ENODEVICE  (-19)
+#define PFT_ECUDA      (-5)
+#define PFT_ENCCL      (-71)
+#define PFT_ESTATE     (-1)
+
+/* pft_solve return codes */
+#define PFT_SOLVE_DONE         0   /* RK_MPI_SA_solve: 0 */
+#define PFT_SOLVE_INTERRUPTED  1   /* RK_MPI_SA_solve: 1 (service callback asked to stop) */
+#define PFT_SOLVE_BUDGET       2   /* extension: max_attempts reached, state resumable */
+#define PFT_SOLVE_BADSYSTEM  (-2)  /* RK_MPI_SA_solve: -2 */
+#define PFT_SOLVE_NAN        (-4)  /* RK_MPI_SA_solve: -4 */
+
+/* flags for pft_create */
+#define PFT_FLAG_NO_FLUX_SHARING  1u   /* every cell recomputes its six face fluxes (debug / A-B) */
+#define PFT_FLAG_NO_SPECULATION   2u   /* do not launch the next K1 before the step-size decision */
+#define PFT_FLAG_RECOMPUTE_K1     4u   /* recompute K1 after a rejected attempt, like the reference */
+
+typedef struct pft_solver pft_solver;
+
+/* one block (z-slab) of the grid; field meaning as in intertrack.c */
+typedef struct {
+	int n1, n2, n3;          /* interior nodes of this block (n3 = slab depth) */
+	int total_n3;            /* interior nodes of the whole grid along z */
+	int first_row;           /* global z index of local row 0 (intertrack.c:1780-1787) */
+	int rank, nranks;        /* slab position; rank 0 owns the z-front, nranks-1 the z-rear */
+	int calc_mode;           /* 0 GradP, 1 SigmaP1-P, 2 temperature model, 10/11 = 0/1 without heat equation */
+	double L1, L2, L3;       /* domain size */
+	double param[PFT_NPARAM];/* model_parameters[], model.c:44-59 order */
+} pft_case;
+
+/* service callback: RK_MPI_S_SOLUTION.Service_Callback (RK_MPI_SAsolver.h:266-279) */
+typedef int (*pft_service_fn)(double final_time, double t, double h, long steps, long steps_total, void *ctx);
+
+/* integration state: the scalar members of RK_MPI_S_SOLUTION (RK_MPI_SAsolver.h:196-289) */
+typedef struct {
+	double t;                /* in/out: current time level */
+	double h;                /* in/out: time step (same hand-over rules as the reference) */
+	double h_min;            /* steps shorter than this are always accepted */
+	double delta;            /* error tolerance */
+	int    delta_local;      /* 1 = DELTA_LOCAL, 0 = DELTA_GLOBAL */
+	long   steps;            /* += accepted steps */
+	long   steps_total;      /* += step attempts */
+	pft_service_fn service;  /* may be NULL */
+	void  *service_ctx;
+	int    handle_nan;       /* RK_MPI_SA_handle_NAN */
+	int    last_nan;         /* RK_MPI_SA_check_NAN */
+	long   max_attempts;     /* extension: stop after this many attempts (<= 0: unlimited) */
+	long   rhs_evals;        /* += right-hand-side evaluations actually performed on the device */
+} pft_system;
+
+typedef struct {
+	long   kernel_launches;  /* kernels of this library launched so far */
+	long   rhs_evals;
+	long   attempts, accepted;
+	double device_ms_total;  /* device time of the last pft_solve (CUDA events on the solver stream) */
+	double stage_ms[5];      /* device time per Merson stage kernel, summed over the last pft_solve
+	                            (only collected when PFT_PROFILE_STAGES=1) */
+	long   stage_launches[5];
+	int    tile_x, tile_y, z_chunk, threads, grid_blocks;
+	long   bytes_per_field;  /* device bytes of one field array incl. ghost planes */
+} pft_stats;
+
+const char *pft_last_error(void);
+const char *pft_version(void);
+
+int pft_create(const pft_case *c, int device, unsigned flags, pft_solver **out);
+int pft_destroy(pft_solver *s);
+
+/* host array in the reference's padded layout: 3 * N1*N2*N3 doubles, N_d = n_d + 2*PFT_BT */
+int pft_upload(pft_solver *s, const double *x_padded);
+int pft_download(pft_solver *s, double *x_padded);          /* writes interior nodes only */
+/* compact interior arrays [n3][n2][n1]; any pointer may be NULL to skip that field */
+int pft_upload_interior(pft_solver *s, const double *u, const double *p, const double *gl);
+int pft_download_interior(pft_solver *s, double *u, double *p, double *gl);
+
+/* gl := max(gl, 0.5*(1 - tanh(0.5/xi_gl*(|x-c|+1e-10 - R)))) on the device (device tanh: <= 2 ulp from libm) */
+int pft_rasterise(pft_solver *s, const double *xyz_raw, int count);
+
+/* dw = f(t, w): upload w, one device RHS evaluation, download; both in the padded layout */
+int pft_rhs_host(pft_solver *s, double t, const double *w_padded, double *dw_padded);
+
+/* integrate the device-resident state to final_time; see RK_MPI_SA_solve for the semantics */
+int pft_solve(pft_solver *s, pft_system *sys, double final_time);
+
+/* mean(p > 0.5) over this block's interior, computed on the device */
+int pft_ice_fraction(pft_solver *s, double *fraction);
+
+/* multi-GPU (one process per GPU): create a 128-byte communicator id on one rank, distribute it
+ * by any means (MPI_Bcast / torch.distributed), then call pft_comm_init on every rank. */
+int pft_comm_unique_id(void *id128);
+int pft_comm_init(pft_solver *s, const void *id128);
+
+int pft_get_stats(pft_solver *s, pft_stats *out);
+int pft_reset_stats(pft_solver *s);
+
+/* debug/test hook: copy an internal array pair (u,p components) to compact host arrays.
+ * which: 0 x, 1 K1, 2 aux3 (stage-3 input), 3 K3, 4 K4, 5 x_new (last attempt's candidate) */
+int pft_debug_fetch(pft_solver *s, int which, double *u, double *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFT_B200_H */

@@ -266,8 +266,15 @@ class Reference:
         p = np.ascontiguousarray(p, dtype=np.float64)
         gl = np.ascontiguousarray(gl, dtype=np.float64)
         par = np.ascontiguousarray(case.param)
+        if spheres_path is None:
+            # the reference aborts the process when the sphere file is missing (equation.c:491-499):
+            # hand it an empty pack (gl is then taken as given)
+            import tempfile
+            f = tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False)
+            f.close()
+            spheres_path = f.name
         rc = self.lib.pftref_setup(case.n1, case.n2, case.total_n3, case.L1, case.L2, case.L3, _ptr(par), case.calc_mode,
-                                   (spheres_path or "/nonexistent").encode(), _ptr(u), _ptr(p), _ptr(gl),
+                                   spheres_path.encode(), _ptr(u), _ptr(p), _ptr(gl),
                                    t0, tau, tau_min, delta, int(use_callback))
         if rc:
             raise RuntimeError(f"pftref_setup failed: {rc}")

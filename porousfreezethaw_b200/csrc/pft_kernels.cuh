@@ -1,0 +1,520 @@
+// pft_kernels.cuh -- sm_100a device code of the PorousFreezeThaw hot path (float64).
+//
+// One kernel template, `merson_stage<STAGE, MODEL, HEAT, SHARE>`, evaluates the right-hand
+// side f (reference: apps/intertrack-hybrid-S-freezing/equation.c:566-741 for MODEL 0/1,
+// :745-884 for MODEL 2) on the stage input of Merson stage STAGE and fuses the stage
+// combination that FOLLOWS it (reference: modules/RK_MPI_SAsolver_hybrid2/
+// RK_MPI_SAsolver_hybrid2.c:378-450 combinations, :508-524 error estimate, :657-668 update):
+//
+//   STAGE 1:  K1 = f(x)                                               -> K1
+//   STAGE 2:  K2 = f(K1*h3 + x)              (input formed on the fly) -> aux3 = (K1+K2)*h6 + x
+//   STAGE 3:  K3 = f(aux3)                                            -> K3
+//   STAGE 4:  K4 = f((K1 + 3.0*K3)*h8 + x)   (on the fly)              -> K4
+//   STAGE 5:  K5 = f((0.5*K1 - 1.5*K3 + 2.0*K4)*h + x) (on the fly)    -> eps = max|0.2K1-0.9K3+0.8K4-0.1K5|,
+//                                                                        x_new = x + h3*(0.5*(K1+K5) + 2.0*K4)
+//
+// Arithmetic is strict IEEE-754 double in the reference's association order: this file must be
+// compiled with -fmad=false (the build defines PFT_STRICT_FP together with that flag).  Values
+// shared between neighbouring cells (face fluxes lambda_face*(u_b-u_a)) are bit-identical to what
+// each cell would compute on its own, because the reference evaluates a face from the lower
+// cell's '+' side and from the upper cell's '-' side with the same operand order.
+//
+// Data layout in HBM (per field, per array): (n3+2) z-planes of n2 rows of `px` doubles,
+// px = n1 rounded up to 4; plane 0 and plane n3+1 are z-ghost planes that hold the neighbouring
+// slab's boundary plane (multi-GPU).  No x/y ghosts are stored: zero-Neumann mirroring is a
+// clamped neighbour index (value-identical, equation.c:142-160), the z-front mirror likewise, and
+// the z-rear Dirichlet temperature is a kernel argument (equation.c:96-111,175-183).
+//
+// Thread mapping: a CTA owns a TX x TY tile of (x,y) and marches a chunk of z-planes; each thread
+// keeps the z-1/z/z+1 values of its column in registers, the current plane's in-plane neighbours
+// come from a double-buffered shared-memory tile with a one-cell halo ring.
+#pragma once
+
+#ifndef PFT_STRICT_FP
+#error "pft_kernels.cuh must be compiled with -fmad=false -DPFT_STRICT_FP (strict IEEE association)"
+#endif
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+// dynamic shared memory (tests/cuda_emu/ redefines this for its CPU emulation of the kernels)
+#ifndef PFT_DYN_SMEM
+#define PFT_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+
+namespace pft {
+
+struct Consts {
+	double h1_2, h2_2, h3_2, h1_d2, h2_d2, h3_d2;      // equation.c:605-612
+	double xi_2_inv_a, bam, sam, eps2_3, eps3_2;       // :442-447; bam=(b*alpha)*mu, sam=(xi_inv_b_sqrt_a2*alpha)*mu
+	double p_eps0, p_eps1;
+	double alpha, zeta, L, u_star, gamma;
+	double g_rho, i_rho, w_rho, g_cp, i_cp, w_cp, g_lam, i_lam, w_lam;
+};
+
+struct Geom {
+	int n1, n2, n3, px;
+	long long plane;          // n2 * px
+	int front, rear;          // this slab owns the physical z-front / z-rear boundary
+	int zc;                   // planes per z-chunk (gridDim.z chunks)
+};
+
+// device-resident control block of the error reduction / step acceptance
+struct Ctl {
+	unsigned long long eps_bits;   // running max of the error estimate (bit pattern of a non-negative double)
+	unsigned int ticket;           // finished-CTA counter of the current stage-5 launch
+	int accept;                    // decision of the last attempt (read by the speculative stage 1)
+	int nonfinite;                 // a non-finite error component was seen (NaN handling)
+	int pad;
+};
+
+// host-mapped result slot (pinned, zero-copy): written by the last CTA of stage 5
+struct HostSlot {
+	unsigned long long seq;
+	double eps;
+	int accept;
+	int nonfinite;
+};
+
+struct StageArgs {
+	const double *xu, *xp, *gl;                 // step-start state (u, p) and the static glass field
+	const double *k1u, *k1p, *k3u, *k3p, *k4u, *k4p;
+	const double *au, *ap;                      // stage 3: the stored stage input (aux3)
+	double *ou, *op;                            // output pair
+	double ha, hb;                              // stage 2: h3,h6   stage 4: h8   stage 5: h,h3
+	double dir_u;                               // Dirichlet temperature at this stage's time level
+	// stage 5 only
+	double delta, h_abs, h_min, eps_scale;      // eps_scale = |h3| for DELTA_LOCAL else 1 (applied as a multiply only if != 1)
+	int scale_eps, handle_nan;
+	Ctl *ctl;
+	HostSlot *slot;
+	unsigned long long seq;
+	unsigned int nblocks;
+	// stage 1 only: run only if *cond != 0 (speculative launch before the host's decision)
+	const int *cond;
+};
+
+struct KParams {
+	Consts c;
+	Geom g;
+	StageArgs a;
+};
+
+// ----------------------------------------------------------------------------------------
+// constitutive laws (equation.c:341-388, 410-421)
+
+__device__ __forceinline__ double mix3(double p, double gl, double xg, double xi, double xw)
+{
+	return gl * xg + (1.0 - gl) * (p * xi + (1.0 - p) * xw);
+}
+
+// lambda(0.5*(pa+pb), 0.5*(ga+gb)) * (-ua + ub): one face of div(lambda grad u), a = lower cell
+__device__ __forceinline__ double face_flux(const Consts &c, double pa, double pb, double ga, double gb, double ua, double ub)
+{
+	double pf = 0.5 * (pa + pb);
+	double gf = 0.5 * (ga + gb);
+	double lam = mix3(pf, gf, c.g_lam, c.i_lam, c.w_lam);
+	return lam * (-ua + ub);
+}
+
+__device__ __forceinline__ double sshape(const Consts &c, double x)
+{
+	double y = x - c.p_eps0;
+	double r = y * y * (c.eps2_3 - c.eps3_2 * y);
+	r = (x >= c.p_eps1) ? 1.0 : r;
+	r = (x <= c.p_eps0) ? 0.0 : r;
+	return r;
+}
+
+// ----------------------------------------------------------------------------------------
+// stage input ("state") formation
+
+template <int STAGE, bool HEAT>
+struct Raw {      // what has to be remembered of a centre cell until its outputs are formed
+	double xu, xp, k1u, k1p, k3u, k3p, k4u, k4p;
+};
+
+// Loads the stage input (su, sp) at linear index `idx`; fills `r` with the operands the output
+// combination needs (only touched members are kept alive by the compiler).
+template <int STAGE, bool HEAT, bool KEEP>
+__device__ __forceinline__ void load_state(const StageArgs &a, long long idx, double &su, double &sp, Raw<STAGE, HEAT> &r)
+{
+	if (STAGE == 1) {
+		su = a.xu[idx];
+		sp = a.xp[idx];
+	} else if (STAGE == 3) {
+		sp = a.ap[idx];
+		su = HEAT ? a.au[idx] : a.xu[idx];
+	} else if (STAGE == 2) {
+		double xp = a.xp[idx], k1p = a.k1p[idx];
+		sp = k1p * a.ha + xp;                                   // :388  q = v*h3 + w
+		double xu = a.xu[idx];
+		if (HEAT) { double k1u = a.k1u[idx]; su = k1u * a.ha + xu; if (KEEP) r.k1u = k1u; }
+		else su = xu;
+		if (KEEP) { r.xu = xu; r.xp = xp; r.k1p = k1p; }
+	} else if (STAGE == 4) {
+		double xp = a.xp[idx], k1p = a.k1p[idx], k3p = a.k3p[idx];
+		sp = (k1p + 3.0 * k3p) * a.ha + xp;                     // :428
+		double xu = a.xu[idx];
+		if (HEAT) { double k1u = a.k1u[idx], k3u = a.k3u[idx]; su = (k1u + 3.0 * k3u) * a.ha + xu; }
+		else su = xu;
+	} else {
+		double xp = a.xp[idx], k1p = a.k1p[idx], k3p = a.k3p[idx], k4p = a.k4p[idx];
+		sp = (0.5 * k1p - 1.5 * k3p + 2.0 * k4p) * a.ha + xp;   // :449
+		double xu = a.xu[idx];
+		if (HEAT) {
+			double k1u = a.k1u[idx], k3u = a.k3u[idx], k4u = a.k4u[idx];
+			su = (0.5 * k1u - 1.5 * k3u + 2.0 * k4u) * a.ha + xu;
+			if (KEEP) { r.k1u = k1u; r.k3u = k3u; r.k4u = k4u; }
+		} else su = xu;
+		if (KEEP) { r.xu = xu; r.xp = xp; r.k1p = k1p; r.k3p = k3p; r.k4p = k4p; }
+	}
+}
+
+// ----------------------------------------------------------------------------------------
+
+// MODEL: 0 GradP (calc_mode 0/10), 1 SigmaP1-P (1/11), 2 temperature model (2)
+// HEAT : the heat equation is active (false for calc_mode 10/11: du/dt = 0, u is static)
+// SHARE: each cell computes its three '+' face fluxes and takes the '-' ones from its neighbours
+template <int STAGE, int MODEL, bool HEAT, bool SHARE>
+__global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ KParams P)
+{
+	const Consts &c = P.c;
+	const Geom &g = P.g;
+	const StageArgs &a = P.a;
+
+	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) return; }
+
+	constexpr int NF = HEAT ? 3 : 1;        // fields kept in the shared tile: p [, u, gl]
+	constexpr bool FLUX = HEAT && SHARE;
+
+	const int TX = blockDim.x, TY = blockDim.y;
+	const int tx = threadIdx.x, ty = threadIdx.y;
+	const int tid = ty * TX + tx;
+	const int SP = TX + 2;                  // tile pitch incl. halo ring
+	const int TS = SP * (TY + 2);           // one field of one buffer
+
+	PFT_DYN_SMEM(double, smem);
+	double *tile = smem;                                    // [2][NF][TS]
+	double *fxs = smem + 2 * NF * TS;                       // [TY][TX+1]  (FLUX)
+	double *fys = fxs + (FLUX ? TY * (TX + 1) : 0);         // [TY+1][TX]  (FLUX)
+
+	const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+	const int i = i0 + tx, j = j0 + ty;
+	const bool active = (i < g.n1) && (j < g.n2);
+	const int ic = min(i, g.n1 - 1), jc = min(j, g.n2 - 1);
+	const long long col = (long long)jc * g.px + ic;        // in-plane offset of this thread's column
+
+	const int k0 = blockIdx.z * g.zc;
+	const int k1 = min(g.n3, k0 + g.zc);
+
+	// halo-ring duty: the first 2*TX+2*TY threads each fetch one ring cell per plane
+	const int nh = 2 * TX + 2 * TY;
+	const bool hduty = tid < nh;
+	int hs = 0;             // slot in the tile
+	long long hcol = 0;     // in-plane offset of the ring cell (clamped = mirrored)
+	if (hduty) {
+		int hx, hy;
+		if (tid < TX) { hx = tid; hy = -1; }
+		else if (tid < 2 * TX) { hx = tid - TX; hy = TY; }
+		else if (tid < 2 * TX + TY) { hx = -1; hy = tid - 2 * TX; }
+		else { hx = TX; hy = tid - 2 * TX - TY; }
+		int gi = min(max(i0 + hx, 0), g.n1 - 1), gj = min(max(j0 + hy, 0), g.n2 - 1);
+		hcol = (long long)gj * g.px + gi;
+		hs = (hy + 1) * SP + (hx + 1);
+	}
+	const int cs = (ty + 1) * SP + (tx + 1);  // this thread's own slot
+
+	// face duty (FLUX): the tile's west and south boundary faces
+	const bool fduty = FLUX && tid < TX + TY;
+
+	Raw<STAGE, HEAT> rc = {}, rn = {}, rdummy = {};
+	double um, pm, gm;       // plane k-1
+	double uc, pc, gc;       // plane k
+	double un, pn, gn;       // plane k+1
+	double fzm = 0.0;        // flux through the face between plane k-1 and k
+	double emax = 0.0;
+	int nonfinite = 0;
+
+	// ---- prologue: planes k0-1 (registers) and k0 (registers + tile 0)
+	{
+		const long long base = (long long)(k0 + 1) * g.plane;
+		load_state<STAGE, HEAT, true>(a, base + col, uc, pc, rc);
+		gc = a.gl[base + col];
+		if (k0 == 0 && g.front) { um = uc; pm = pc; gm = gc; }          // z-front mirror (equation.c:164-174)
+		else {
+			load_state<STAGE, HEAT, false>(a, base - g.plane + col, um, pm, rdummy);
+			gm = a.gl[base - g.plane + col];
+		}
+		double *t0 = tile;
+		t0[cs] = pc;
+		if (HEAT) { t0[TS + cs] = uc; t0[2 * TS + cs] = gc; }
+		if (hduty) {
+			double hu, hp;
+			load_state<STAGE, HEAT, false>(a, base + hcol, hu, hp, rdummy);
+			t0[hs] = hp;
+			if (HEAT) { t0[TS + hs] = hu; t0[2 * TS + hs] = a.gl[base + hcol]; }
+		}
+		if (HEAT) fzm = face_flux(c, pm, pc, gm, gc, um, uc);
+	}
+
+	int cur = 0;
+	for (int k = k0; k < k1; ++k) {
+		const long long base_n = (long long)(k + 2) * g.plane;      // plane k+1
+		const bool top = (k + 1 == g.n3) && g.rear;                   // plane k+1 is the physical z-rear ghost
+		const bool more = (k + 1 < k1);
+
+		// ---- fetch plane k+1 (kept in registers until the end of the iteration)
+		double hu = 0.0, hp = 0.0, hg = 0.0;
+		if (top) {
+			un = a.dir_u; pn = pc; gn = gc;                           // equation.c:175-183 / :251-261
+		} else {
+			load_state<STAGE, HEAT, true>(a, base_n + col, un, pn, rn);
+			gn = a.gl[base_n + col];
+		}
+		if (more && hduty) {
+			load_state<STAGE, HEAT, false>(a, base_n + hcol, hu, hp, rdummy);
+			if (HEAT) hg = a.gl[base_n + hcol];
+		}
+
+		__syncthreads();                                             // tile[cur] complete
+		const double *tp = tile + cur * NF * TS;
+		const double *tu = tp + TS, *tg = tp + 2 * TS;
+
+		const double pw = tp[cs - 1], pe = tp[cs + 1], ps = tp[cs - SP], pnn = tp[cs + SP];
+
+		double sum = 0.0;        // h1_2*(...) + h2_2*(...) + h3_2*(...) of div(lambda grad u)
+		if (HEAT) {
+			const double ue = tu[cs + 1], ge = tg[cs + 1];
+			const double unn = tu[cs + SP], gnn = tg[cs + SP];
+			double fe = face_flux(c, pc, pe, gc, ge, uc, ue);
+			double fn = face_flux(c, pc, pnn, gc, gnn, uc, unn);
+			double fzp = face_flux(c, pc, pn, gc, gn, uc, un);
+			double fw, fs;
+			if (FLUX) {
+				fxs[ty * (TX + 1) + tx + 1] = fe;
+				fys[(ty + 1) * TX + tx] = fn;
+				if (fduty) {
+					if (tid < TY) {          // west boundary face of row `tid`
+						int s0 = (tid + 1) * SP;
+						fxs[tid * (TX + 1)] = face_flux(c, tp[s0], tp[s0 + 1], tg[s0], tg[s0 + 1], tu[s0], tu[s0 + 1]);
+					} else {                 // south boundary face of column `tid-TY`
+						int s0 = (tid - TY) + 1;
+						fys[tid - TY] = face_flux(c, tp[s0], tp[s0 + SP], tg[s0], tg[s0 + SP], tu[s0], tu[s0 + SP]);
+					}
+				}
+				__syncthreads();
+				fw = fxs[ty * (TX + 1) + tx];
+				fs = fys[ty * TX + tx];
+			} else {
+				const double uw = tu[cs - 1], gw = tg[cs - 1];
+				const double us = tu[cs - SP], gs = tg[cs - SP];
+				fw = face_flux(c, pw, pc, gw, gc, uw, uc);
+				fs = face_flux(c, ps, pc, gs, gc, us, uc);
+			}
+			sum = c.h1_2 * (-fw + fe) + c.h2_2 * (-fs + fn) + c.h3_2 * (-fzm + fzp);   // equation.c:711-720
+			fzm = fzp;
+		}
+
+		double du, dp;
+		if (MODEL == 2) {
+			// equation.c:835-867
+			double rho = mix3(pc, gc, c.g_rho, c.i_rho, c.w_rho);
+			double cp = mix3(pc, gc, c.g_cp, c.i_cp, c.w_cp);
+			double ch = cosh(c.gamma * (uc - c.u_star));
+			double dp_du = (-0.5 * c.gamma / (ch * ch)) * fmax(0.0, 1.0 - c.zeta * gc);
+			du = sum / (rho * (cp - c.L * dp_du));
+			dp = dp_du * du;
+		} else {
+			// equation.c:659-694
+			dp = c.h1_2 * (-(-pw + pc) + (-pc + pe))
+			   + c.h2_2 * (-(-ps + pc) + (-pc + pnn))
+			   + c.h3_2 * (-(-pm + pc) + (-pc + pn));
+			double one_m_p = 1.0 - pc;
+			double well = c.xi_2_inv_a * pc * one_m_p * (pc - 0.5);
+			double du_star = uc - c.u_star;
+			if (MODEL == 0) {
+				double gx = c.h1_d2 * (-pw + pe), gy = c.h2_d2 * (-ps + pnn), gz = c.h3_d2 * (-pm + pn);
+				double nrm = sqrt(gx * gx + gy * gy + gz * gz) + 1E-10;               // :332-336
+				dp += well - c.bam * nrm * du_star;                                       // :370
+			} else {
+				dp += well - c.sam * sshape(c, pc) * sshape(c, one_m_p) * fmax(pc * one_m_p, 0.0) * du_star;   // :387
+			}
+			dp /= c.alpha;
+			dp *= fmax(0.0, 1.0 - c.zeta * gc);
+			if (HEAT) {
+				double rho = mix3(pc, gc, c.g_rho, c.i_rho, c.w_rho);
+				double cp = mix3(pc, gc, c.g_cp, c.i_cp, c.w_cp);
+				du = (sum / rho + c.L * dp) / cp;                                         // :711-723
+			} else du = 0.0;
+		}
+
+		// ---- fused combination that follows this stage
+		if (active) {
+			const long long o = (long long)(k + 1) * g.plane + col;
+			if (STAGE == 1 || STAGE == 3 || STAGE == 4) {
+				a.op[o] = dp;
+				if (HEAT) a.ou[o] = du;
+			} else if (STAGE == 2) {
+				a.op[o] = (rc.k1p + dp) * a.hb + rc.xp;                                   // :408
+				if (HEAT) a.ou[o] = (rc.k1u + du) * a.hb + rc.xu;
+			} else {
+				double e = fabs(0.2 * rc.k1p - 0.9 * rc.k3p + 0.8 * rc.k4p - 0.1 * dp);   // :521
+				if (!(e <= 1.7976931348623157e308)) nonfinite = 1;
+				emax = (e > emax) ? e : emax;
+				a.op[o] = rc.xp + a.hb * (0.5 * (rc.k1p + dp) + 2.0 * rc.k4p);            // :667
+				if (HEAT) {
+					double eu = fabs(0.2 * rc.k1u - 0.9 * rc.k3u + 0.8 * rc.k4u - 0.1 * du);
+					if (!(eu <= 1.7976931348623157e308)) nonfinite = 1;
+					emax = (eu > emax) ? eu : emax;
+					a.ou[o] = rc.xu + a.hb * (0.5 * (rc.k1u + du) + 2.0 * rc.k4u);
+				}
+			}
+		}
+
+		// ---- publish plane k+1 into the other tile buffer, rotate the register window
+		if (more) {
+			double *tn = tile + (cur ^ 1) * NF * TS;
+			tn[cs] = pn;
+			if (HEAT) { tn[TS + cs] = un; tn[2 * TS + cs] = gn; }
+			if (hduty) {
+				tn[hs] = hp;
+				if (HEAT) { tn[TS + hs] = hu; tn[2 * TS + hs] = hg; }
+			}
+		}
+		um = uc; pm = pc; gm = gc;
+		uc = un; pc = pn; gc = gn;
+		rc = rn;
+		cur ^= 1;
+	}
+
+	// ---- stage 5: grid-wide max of the error estimate, acceptance decision, host notification
+	if (STAGE == 5) {
+		// CTA max through a shared-memory atomic on the bit pattern (non-negative doubles order
+		// like their uint64 patterns; the tile need not be a multiple of the warp size)
+		__shared__ unsigned long long s_bits;
+		__shared__ int s_nonfinite;
+		if (tid == 0) { s_bits = 0ull; s_nonfinite = 0; }
+		__syncthreads();
+		if (emax > 0.0) atomicMax(&s_bits, (unsigned long long)__double_as_longlong(emax));
+		if (nonfinite) atomicOr(&s_nonfinite, 1);
+		__syncthreads();
+		if (tid == 0) {
+			Ctl *ctl = a.ctl;
+			if (s_bits) atomicMax(&ctl->eps_bits, s_bits);
+			if (s_nonfinite) atomicOr(&ctl->nonfinite, 1);
+			__threadfence();
+			unsigned int t = atomicAdd(&ctl->ticket, 1u);
+			if (t == a.nblocks - 1) {            // last CTA of the launch: every other CTA's max is in
+				__threadfence();
+				unsigned long long bits = atomicMax(&ctl->eps_bits, 0ull);
+				int nfl = atomicOr(&ctl->nonfinite, 0);
+				double eps = __longlong_as_double((long long)bits);
+				double ecmp = a.scale_eps ? eps * a.eps_scale : eps;            // RK_MPI_SAsolver_hybrid2.c:578
+				int acc = (ecmp < a.delta) || (a.h_abs < a.h_min);               // :599
+				if (a.handle_nan && nfl) acc = 0;                                 // :626-646
+				ctl->accept = acc;
+				ctl->eps_bits = 0ull;
+				ctl->nonfinite = 0;
+				ctl->ticket = 0u;
+				__threadfence();
+				HostSlot *s = a.slot;
+				s->eps = eps;
+				s->accept = acc;
+				s->nonfinite = nfl;
+				__threadfence_system();
+				*(volatile unsigned long long *)&s->seq = a.seq;
+				__threadfence_system();
+			}
+		}
+	}
+}
+
+// ----------------------------------------------------------------------------------------
+// layout conversion between the reference's padded host layout (staged in device memory) and the
+// compact device layout
+
+// dir 0: padded -> compact (interior only), dir 1: compact -> padded (interior only)
+__global__ void repack_kernel(double *padded, double *compact, int n1, int n2, int n3, int px, long long plane,
+                              int N1, long long rowsize, int bt, int dir)
+{
+	const long long total = (long long)n1 * n2 * n3;
+	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+		int i = (int)(t % n1);
+		long long r = t / n1;
+		int j = (int)(r % n2);
+		int k = (int)(r / n2);
+		long long ip = (long long)(k + bt) * rowsize + (long long)(j + bt) * N1 + bt + i;
+		long long ic = (long long)(k + 1) * plane + (long long)j * px + i;
+		if (dir == 0) compact[ic] = padded[ip];
+		else padded[ip] = compact[ic];
+	}
+}
+
+// dense [n3][n2][n1] <-> compact device layout
+__global__ void dense_kernel(double *dense, double *compact, int n1, int n2, int n3, int px, long long plane, int dir)
+{
+	const long long total = (long long)n1 * n2 * n3;
+	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+		int i = (int)(t % n1);
+		long long r = t / n1;
+		int j = (int)(r % n2);
+		int k = (int)(r / n2);
+		long long ic = (long long)(k + 1) * plane + (long long)j * px + i;
+		if (dir == 0) compact[ic] = dense[t];
+		else dense[t] = compact[ic];
+	}
+}
+
+// sphere rasteriser (equation.c:508-529): gl = max(gl, 0.5*(1 - tanh(0.5/xi_gl*(|x-c| + 1e-10 - R))))
+__global__ void rasterise_kernel(double *gl, const double *bx, const double *by, const double *bz, int count,
+                                 int n1, int n2, int n3, int px, long long plane, int first_row, int total_n3,
+                                 double L1, double L2, double L3, double xi_gl, double radius)
+{
+	PFT_DYN_SMEM(double, sb);           // staged sphere centres, `chunk` at a time
+	const int chunk = blockDim.x;
+	const long long total = (long long)n1 * n2 * n3;
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = t < total;
+	int i = 0, j = 0, k = 0;
+	if (valid) { i = (int)(t % n1); long long r = t / n1; j = (int)(r % n2); k = (int)(r / n2); }
+	const double x = L1 * (0.5 + i) / n1;
+	const double y = L2 * (0.5 + j) / n2;
+	const double z = L3 * (0.5 + k + first_row) / total_n3;
+	const long long ic = (long long)(k + 1) * plane + (long long)j * px + i;
+	double v = valid ? gl[ic] : 0.0;
+	const double s = 0.5 / xi_gl;
+	// a sphere further than R + 40*xi_gl contributes < 1e-17: skip its tanh (result-neutral below 1 ulp of 1)
+	for (int q0 = 0; q0 < count; q0 += chunk) {
+		int q = q0 + threadIdx.x;
+		__syncthreads();
+		if (q < count) { sb[threadIdx.x] = bx[q]; sb[chunk + threadIdx.x] = by[q]; sb[2 * chunk + threadIdx.x] = bz[q]; }
+		__syncthreads();
+		int m = min(chunk, count - q0);
+		for (int qq = 0; qq < m; ++qq) {
+			double dx = x - sb[qq], dy = y - sb[chunk + qq], dz = z - sb[2 * chunk + qq];
+			double d = sqrt(dx * dx + dy * dy + dz * dz) + 1E-10;
+			double f = 0.5 * (1.0 - tanh(s * (d - radius)));
+			v = (v < f) ? f : v;
+		}
+	}
+	if (valid) gl[ic] = v;
+}
+
+// count of interior nodes with p > 0.5 (scripts/avg.sh:9-20)
+__global__ void ice_count_kernel(const double *p, int n1, int n2, int n3, int px, long long plane, unsigned long long *count)
+{
+	const long long total = (long long)n1 * n2 * n3;
+	unsigned long long local = 0;
+	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+		int i = (int)(t % n1);
+		long long r = t / n1;
+		int j = (int)(r % n2);
+		int k = (int)(r / n2);
+		if (p[(long long)(k + 1) * plane + (long long)j * px + i] > 0.5) local++;
+	}
+	if (local) atomicAdd(count, local);
+}
+
+}  // namespace pft

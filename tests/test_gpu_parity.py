@@ -1,0 +1,238 @@
+"""GPU parity tests (run on a B200 with -m gpu): the nvcc-built sm_100a library, called through
+the C ABI, against the oracle on identical seeded inputs.
+
+Bit-exact for calc_mode 0/1/10/11; calc_mode 2 (device cosh) within rel. L_inf 1e-10 / +-1% steps.
+Full-size cases (200x200x400 = BASELINE's "400" case) are checked through size-independent
+properties: tiling/chunking invariance, flux-sharing on/off, K1 reuse on/off, interrupted vs
+uninterrupted integration -- all bit-exact -- plus conservation-type sanity."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from oracle import pyoracle as po
+from porousfreezethaw_b200 import cases
+from porousfreezethaw_b200.solver import SlabSolver, FLAG_NO_FLUX_SHARING, FLAG_NO_SPECULATION, FLAG_RECOMPUTE_K1
+
+pytestmark = pytest.mark.gpu
+
+
+def _real_spheres(spec):
+    f = po.spheres_file()
+    if f:
+        spec.spheres = np.loadtxt(f).reshape(-1, 3)
+    else:
+        spec.spheres = cases.synthetic_spheres(200, zmax=1.6)
+    return spec
+
+
+@pytest.mark.parametrize("mode", [0, 1, 10, 11])
+def test_rhs_bit_exact(gpu_lib, mode):
+    parity.check_rhs(cases.small_case(24, 20, 32, calc_mode=mode), gpu_lib)
+
+
+def test_rhs_mode2_tolerance(gpu_lib):
+    parity.check_rhs(cases.small_case(24, 20, 32, calc_mode=2), gpu_lib, exact=False)
+
+
+@pytest.mark.parametrize("mode,flags", [(0, 0), (0, FLAG_NO_FLUX_SHARING), (1, 0), (10, 0), (11, 0)])
+def test_fused_stages_bit_exact(gpu_lib, mode, flags):
+    parity.check_fused_stages(cases.small_case(24, 20, 32, calc_mode=mode), gpu_lib, flags=flags)
+
+
+def test_fused_stages_mode2(gpu_lib):
+    parity.check_fused_stages(cases.small_case(24, 20, 32, calc_mode=2), gpu_lib, exact=False)
+
+
+@pytest.mark.parametrize("tx,ty,zc", [(5, 4, 3), (32, 8, 2), (7, 9, 5), (64, 8, 1)])
+def test_ragged_tiles_and_chunks(gpu_lib, monkeypatch, tx, ty, zc):
+    """grids that are not multiples of the tile, many tiles, several z-chunks (edge cases)"""
+    monkeypatch.setenv("PFT_TX", str(tx))
+    monkeypatch.setenv("PFT_TY", str(ty))
+    monkeypatch.setenv("PFT_ZCHUNKS", str(zc))
+    spec = cases.small_case(37, 23, 19, calc_mode=0)
+    parity.check_rhs(spec, gpu_lib)
+    parity.check_fused_stages(spec, gpu_lib)
+
+
+def test_minimal_grids(gpu_lib):
+    """smallest sensible blocks: one row / one plane thick"""
+    for n in ((8, 8, 1), (8, 1, 8), (1, 8, 8), (3, 3, 3)):
+        spec = cases.small_case(*n, calc_mode=1, spheres=2)
+        parity.check_rhs(spec, gpu_lib)
+        parity.check_fixed_steps(spec, gpu_lib, nsteps=2)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 10, 11])
+def test_fixed_step_mode(gpu_lib, mode):
+    parity.check_fixed_steps(cases.small_case(24, 20, 32, calc_mode=mode), gpu_lib, nsteps=10)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 10, 11])
+def test_adaptive_sequence_bit_exact(gpu_lib, mode):
+    parity.check_adaptive(cases.small_case(24, 20, 32, calc_mode=mode), gpu_lib, T=60.0, chunks=3, with_service=True)
+
+
+@pytest.mark.parametrize("flags", [FLAG_NO_SPECULATION, FLAG_RECOMPUTE_K1, FLAG_NO_FLUX_SHARING | FLAG_NO_SPECULATION])
+def test_adaptive_variants(gpu_lib, flags):
+    parity.check_adaptive(cases.small_case(24, 20, 32, calc_mode=0), gpu_lib, T=40.0, chunks=2, flags=flags)
+
+
+def test_adaptive_mode2(gpu_lib):
+    parity.check_adaptive(cases.small_case(24, 20, 32, calc_mode=2), gpu_lib, T=60.0, exact=False)
+
+
+def test_case100_first_steps(gpu_lib):
+    """configs[0]: the "100" low-resolution case (50x50x100) with the reference sphere pack:
+    the first attempts of the real run (t = 0 -> 2 s), bit-exact sequence and fields."""
+    spec = _real_spheres(cases.archived_case("100-GradP"))
+    parity.check_adaptive(spec, gpu_lib, T=2.0, chunks=2, with_service=True)
+
+
+def test_case200_rhs_and_steps(gpu_lib):
+    """configs[1]: the "200" medium-resolution case (100x100x200)"""
+    spec = _real_spheres(cases.archived_case("200-GradP"))
+    parity.check_rhs(spec, gpu_lib, perturb=False)
+    parity.check_fixed_steps(spec, gpu_lib, nsteps=3, H=0.01)
+
+
+def test_dirichlet_switch(gpu_lib):
+    """the z-rear Dirichlet temperature switches at phase_switch_time (equation.c:110): stage times
+    straddling the switch must pick the value per stage"""
+    spec = cases.small_case(16, 12, 20, calc_mode=0)
+    spec.params["phase_switch_time"] = 3.0
+    parity.check_adaptive(spec, gpu_lib, T=8.0, chunks=2)
+
+
+def test_callback_break_and_resume(gpu_lib):
+    """Service_Callback returning nonzero -> solve returns 1 with (t, h=new_h) saved
+    (RK_MPI_SAsolver_hybrid2.c:697-705); resuming reaches the same final state as the oracle
+    driven the same way."""
+    spec = cases.small_case(24, 20, 32, calc_mode=0)
+    case, orc, w = parity.make(spec)
+    x = w.copy()
+    s = orc.new_system(t=0.0, h=spec.tau, h_min=spec.tau_min, delta=spec.delta,
+                       service=lambda ft, t, h, st, tot, ctx: int(st % 7 == 0))
+    sol = SlabSolver(spec, lib_path=gpu_lib)
+    sol.upload(w.copy())
+    sol.set_service(lambda ft, t, h, st, tot: int(st % 7 == 0))
+    codes_o, codes_g = [], []
+    for _ in range(6):
+        codes_o.append(orc.solve(s, x, 25.0))
+        r = sol.solve(25.0)
+        codes_g.append(r.code)
+        assert (r.t, r.h, r.steps, r.steps_total) == (s.t, s.h, s.steps, s.steps_total)
+    assert codes_o == codes_g and 1 in codes_g
+    got = w.copy(); sol.download(got); sol.close()
+    parity.assert_fields(case, got, x, True, "callback break/resume")
+
+
+def test_attempt_budget_resume(gpu_lib):
+    """max_attempts (bench extension): stopping every 5 attempts and resuming == one uninterrupted run"""
+    spec = cases.small_case(24, 20, 32, calc_mode=1)
+    case, orc, w = parity.make(spec)
+    a = SlabSolver(spec, lib_path=gpu_lib); a.upload(w.copy())
+    ra = a.solve(40.0)
+    b = SlabSolver(spec, lib_path=gpu_lib); b.upload(w.copy())
+    while True:
+        rb = b.solve(40.0, max_attempts=5)
+        if rb.code != 2:
+            break
+    assert (ra.t, ra.h, ra.steps, ra.steps_total) == (rb.t, rb.h, rb.steps, rb.steps_total)
+    xa, xb = w.copy(), w.copy()
+    a.download(xa); b.download(xb); a.close(); b.close()
+    assert np.array_equal(xa, xb)
+
+
+def test_nan_handling(gpu_lib):
+    """RK_MPI_SA_handle_NAN semantics (hybrid2.c:464-504, 626-646): a step so long that the error
+    estimate overflows is retried with h/10 and last_NAN is raised"""
+    spec = cases.small_case(16, 12, 20, calc_mode=0)
+    case, orc, w = parity.make(spec)
+    x = w.copy()
+    s = orc.new_system(t=0.0, h=1e200, h_min=0.0, delta=spec.delta, handle_nan=True)
+    rc_o = orc.solve(s, x, 1e300)
+    sol = SlabSolver(spec, lib_path=gpu_lib)
+    sol.upload(w.copy())
+    sol.sys.h, sol.sys.h_min, sol.sys.handle_nan = 1e200, 0.0, 1
+    sol.sys.max_attempts = 0
+    s2 = orc.new_system(t=0.0, h=1e200, h_min=0.0, delta=spec.delta, handle_nan=True, max_attempts=12)
+    x2 = w.copy()
+    rc_o = orc.solve(s2, x2, 1e300)
+    r = sol.solve(1e300, max_attempts=12)
+    sol.close()
+    assert r.code == rc_o
+    assert r.last_nan == s2.last_nan == 1
+    assert (r.t, r.h, r.steps, r.steps_total) == (s2.t, s2.h, s2.steps, s2.steps_total)
+
+
+# ---- full-size properties (BASELINE sizes; the oracle would take minutes here) ------------
+
+@pytest.fixture(scope="module")
+def hr_state(gpu_lib):
+    """the "400" high-resolution case (200x200x400, calc_mode 1), 12 attempts in"""
+    spec = _real_spheres(cases.archived_case("400-SigmaP1-P-smallsigma"))
+    sol = SlabSolver(spec, lib_path=gpu_lib)
+    u, p, gl = spec.initial_fields()
+    sol.upload_interior(u, p, gl)
+    sol.rasterise(spec.spheres)
+    u, p, gl = sol.download_interior()
+    r = sol.solve(spec.final_time, max_attempts=12)
+    out = sol.download_interior()
+    sol.close()
+    return spec, (u, p, gl), r, out
+
+
+@pytest.mark.parametrize("env,flags", [
+    ({"PFT_TX": "40", "PFT_TY": "12", "PFT_ZCHUNKS": "7"}, 0),
+    ({"PFT_TX": "100", "PFT_TY": "5", "PFT_ZCHUNKS": "1"}, 0),
+    ({}, FLAG_NO_FLUX_SHARING),
+    ({}, FLAG_RECOMPUTE_K1 | FLAG_NO_SPECULATION),
+])
+def test_fullsize_invariance(gpu_lib, hr_state, monkeypatch, env, flags):
+    """results do not depend on tiling, z-chunking, flux sharing, K1 reuse or speculation (bit-exact)"""
+    spec, (u, p, gl), r0, out0 = hr_state
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sol = SlabSolver(spec, lib_path=gpu_lib, flags=flags)
+    sol.upload_interior(u, p, gl)
+    r = sol.solve(spec.final_time, max_attempts=12)
+    out = sol.download_interior()
+    sol.close()
+    assert (r.t, r.h, r.steps, r.steps_total) == (r0.t, r0.h, r0.steps, r0.steps_total)
+    for a, b in zip(out, out0):
+        assert np.array_equal(a, b)
+
+
+def test_fullsize_sanity(hr_state):
+    spec, (u, p, gl), r, (u1, p1, gl1) = hr_state
+    assert np.array_equal(gl, gl1)                      # the glass field is static (equation.c:731)
+    assert np.isfinite(u1).all() and np.isfinite(p1).all()
+    assert r.steps >= 1 and r.steps_total == 12
+    assert u1.max() <= 293.15 + 1e-9 and u1.min() >= 248.15 - 1e-9      # discrete maximum principle between IC and Dirichlet value
+    assert -1e-6 <= p1.min() and p1.max() <= 1 + 1e-6
+
+
+def test_device_rasteriser_vs_host(gpu_lib):
+    """pft_rasterise (device tanh) against the oracle's host rasteriser: <= 4 ulp of 1.0"""
+    spec = _real_spheres(cases.archived_case("100-GradP"))
+    case, orc, w = parity.make(spec)
+    sol = SlabSolver(spec, lib_path=gpu_lib)
+    u, p, gl = spec.initial_fields()
+    sol.upload_interior(u, p, gl)
+    sol.rasterise(spec.spheres)
+    _, _, gl_dev = sol.download_interior()
+    frac = None
+    sol.close()
+    assert np.abs(gl_dev - case.interior(w)[2]).max() <= 4 * np.finfo(float).eps
+
+
+def test_ice_fraction(gpu_lib):
+    spec = cases.small_case(24, 20, 32, calc_mode=0)
+    case, orc, w = parity.make(spec)
+    sol = SlabSolver(spec, lib_path=gpu_lib)
+    sol.upload(w.copy())
+    f = sol.ice_fraction()
+    sol.close()
+    assert f == orc.ice_fraction(w)
