@@ -59,6 +59,7 @@ extern "C" {
 #define PFT_FLAG_NO_FLUX_SHARING  1u   /* every cell recomputes its six face fluxes (debug / A-B) */
 #define PFT_FLAG_NO_SPECULATION   2u   /* do not launch the next K1 before the step-size decision */
 #define PFT_FLAG_RECOMPUTE_K1     4u   /* recompute K1 after a rejected attempt, like the reference */
+#define PFT_FLAG_LEGACY_LOADS     8u   /* per-thread global loads instead of TMA tile staging (debug / A-B) */
 
 typedef struct pft_solver pft_solver;
 

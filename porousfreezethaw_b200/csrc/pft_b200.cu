@@ -17,6 +17,7 @@
 // floating-point expression keeps the reference's association.
 #include "../../include/pft_b200.h"
 #include "pft_kernels.cuh"
+#include "pft_kernels_tma.cuh"
 
 #include <dlfcn.h>
 #include <emmintrin.h>
@@ -165,6 +166,12 @@ struct pft_solver {
 	bool profile;
 	std::vector<StageTimer> timers;
 	pft_stats st;
+	// TMA path (heat modes): one tensor map per array, box = tile + halo ring
+	bool use_tma;
+	CUtensorMap tmap[A_COUNT][2];
+	CUtensorMap tmap_gl;
+	int bx, by, as;
+	size_t smem_tma[5];
 };
 
 static double dirichlet(const pft_solver *s, double t)
@@ -229,6 +236,32 @@ static int choose_chunks(int tiles_xy, int n3, int sms)
 
 // ------------------------------------------------------------------------------------------
 
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D tensor map over one field array: (px, n2, n3+2) doubles, box (bx, by, 1)
+static int make_tensor_map(pft_solver *s, CUtensorMap *m, double *base)
+{
+	static encode_tiled_fn encode = nullptr;
+	if (!encode) {
+		void *fn = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+		if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) return fail(PFT_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+		encode = (encode_tiled_fn)fn;
+	}
+	const Geom &g = s->g;
+	cuuint64_t dim[3] = {(cuuint64_t)g.px, (cuuint64_t)g.n2, (cuuint64_t)(g.n3 + 2)};
+	cuuint64_t strides[2] = {(cuuint64_t)g.px * sizeof(double), (cuuint64_t)g.plane * sizeof(double)};
+	cuuint32_t box[3] = {(cuuint32_t)s->bx, (cuuint32_t)s->by, 1u};
+	cuuint32_t estr[3] = {1u, 1u, 1u};
+	CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dim, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) return fail(PFT_ECUDA, "cuTensorMapEncodeTiled failed (%d) for box %dx%d", (int)r, s->bx, s->by);
+	return 0;
+}
+
 static void make_consts(pft_solver *s)
 {
 	const pft_case &cs = s->cs;
@@ -282,6 +315,28 @@ static cudaError_t launch_stage_t(pft_solver *s, const KParams &kp)
 	return launch_t<STAGE, 1, false, false>(s, kp);
 }
 
+template <int STAGE, int MODEL, bool SHARE>
+static cudaError_t launch_tma_t(pft_solver *s, const TmaParams &kp)
+{
+	auto fn = merson_stage_tma<STAGE, MODEL, SHARE>;
+	static bool attr_set = false;
+	if (!attr_set) {
+		cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+		if (e != cudaSuccess) return e;
+		attr_set = true;
+	}
+	PFT_LAUNCH(fn, s->grid, s->block, s->smem_tma[STAGE - 1], s->stream, kp);
+	return cudaGetLastError();
+}
+
+template <int STAGE>
+static cudaError_t launch_stage_tma_t(pft_solver *s, const TmaParams &kp)
+{
+	if (s->model == 2) return s->share ? launch_tma_t<STAGE, 2, true>(s, kp) : launch_tma_t<STAGE, 2, false>(s, kp);
+	if (s->model == 0) return s->share ? launch_tma_t<STAGE, 0, true>(s, kp) : launch_tma_t<STAGE, 0, false>(s, kp);
+	return s->share ? launch_tma_t<STAGE, 1, true>(s, kp) : launch_tma_t<STAGE, 1, false>(s, kp);
+}
+
 // stage launcher: fills the argument block for one Merson stage and (multi-GPU) exchanges the
 // z-boundary planes of what the stage produced
 static int exchange_pair(pft_solver *s, double *u, double *p);
@@ -316,6 +371,26 @@ static int launch_stage(pft_solver *s, int stage, double t_stage, double ha, dou
 		cudaEventRecord(tm.a, s->stream);
 	}
 	cudaError_t e;
+	if (s->use_tma) {
+		TmaParams tp;
+		tp.c = kp.c; tp.g = kp.g; tp.a = kp.a;
+		tp.bx = s->bx; tp.by = s->by; tp.as = s->as;
+		// array order of a stage: p-type arrays, u-type arrays, gl (pft_kernels_tma.cuh, stage_np)
+		const int src[5][4] = {{xin, -1, -1, -1}, {xin, A_K1, -1, -1}, {A_A3, -1, -1, -1}, {xin, A_K1, A_K3, -1}, {xin, A_K1, A_K3, A_K4}};
+		const int np = stage_np(stage);
+		for (int m = 0; m < np; m++) {
+			tp.maps[m] = s->tmap[src[stage - 1][m]][1];
+			tp.maps[np + m] = s->tmap[src[stage - 1][m]][0];
+		}
+		tp.maps[2 * np] = s->tmap_gl;
+		switch (stage) {
+		case 1: e = launch_stage_tma_t<1>(s, tp); break;
+		case 2: e = launch_stage_tma_t<2>(s, tp); break;
+		case 3: e = launch_stage_tma_t<3>(s, tp); break;
+		case 4: e = launch_stage_tma_t<4>(s, tp); break;
+		default: e = launch_stage_tma_t<5>(s, tp); break;
+		}
+	} else
 	switch (stage) {
 	case 1: e = launch_stage_t<1>(s, kp); break;
 	case 2: e = launch_stage_t<2>(s, kp); break;
@@ -450,6 +525,7 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	choose_tile(cs->n1, cs->n2, max_threads, &s->TX, &s->TY);
 	if (env_int("PFT_TX", 0) > 0) s->TX = env_int("PFT_TX", 0);
 	if (env_int("PFT_TY", 0) > 0) s->TY = env_int("PFT_TY", 0);
+	if (s->TX & 1) s->TX++;                  // tile origins must be even (TMA inner-offset alignment)
 	if (s->TX * s->TY > 512 || s->TX * s->TY < 2 * s->TX + 2 * s->TY) {
 		int tx_ = s->TX, ty_ = s->TY;
 		delete s;
@@ -487,6 +563,29 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	if (e != cudaSuccess) { pft_destroy(s); return fail(PFT_ENOMEM, "cudaMalloc(%zu): %s", fb, cudaGetErrorString(e)); }
 	CU(cudaMemsetAsync(s->gl, 0, fb, s->stream));
 	if (!s->heat) s->arr[A_XN][0] = s->arr[A_X][0];
+
+	s->use_tma = s->heat && !(flags & PFT_FLAG_LEGACY_LOADS) && !env_int("PFT_LEGACY", 0);
+	if (s->use_tma) {
+		s->bx = s->TX + 4;                   // box starts at x = i0-2 (16-byte aligned inner offset), TX is even
+		s->by = s->TY + 2;
+		s->as = (s->bx * s->by + 15) & ~15;  // each array buffer starts 128-byte aligned
+		size_t fl = s->share ? (size_t)s->TY * (s->TX + 1) + (size_t)(s->TY + 1) * s->TX : 0;
+		size_t worst = 0;
+		for (int st = 1; st <= 5; st++) {
+			int na = 2 * stage_np(st) + 1;
+			bool form = !(st == 1 || st == 3);
+			s->smem_tma[st - 1] = ((size_t)TMA_STAGES * na * s->as + (form ? 4 * (size_t)s->as : 0) + fl) * sizeof(double);
+			worst = std::max(worst, s->smem_tma[st - 1]);
+		}
+		if (worst > 225 * 1024) { pft_destroy(s); return fail(PFT_EINVAL, "tile %dx%d needs %zu bytes of shared memory", s->TX, s->TY, worst); }
+		for (int a = 0; a < A_COUNT; a++)
+			for (int q = 0; q < 2; q++) {
+				int rc = make_tensor_map(s, &s->tmap[a][q], s->arr[a][q]);
+				if (rc) { pft_destroy(s); return rc; }
+			}
+		int rc = make_tensor_map(s, &s->tmap_gl, s->gl);
+		if (rc) { pft_destroy(s); return rc; }
+	}
 	CU(cudaMalloc(&s->ctl, sizeof(Ctl)));
 	CU(cudaMemsetAsync(s->ctl, 0, sizeof(Ctl), s->stream));
 	CU(cudaMalloc(&s->red, 2 * sizeof(double)));
@@ -911,6 +1010,8 @@ done:
 	if (xc != A_X) {
 		std::swap(s->arr[A_X][0], s->arr[A_XN][0]);
 		std::swap(s->arr[A_X][1], s->arr[A_XN][1]);
+		std::swap(s->tmap[A_X][0], s->tmap[A_XN][0]);
+		std::swap(s->tmap[A_X][1], s->tmap[A_XN][1]);
 	}
 	return ret;
 

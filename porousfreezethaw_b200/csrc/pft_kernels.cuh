@@ -41,6 +41,7 @@
 // dynamic shared memory (tests/cuda_emu/ redefines this for its CPU emulation of the kernels)
 #ifndef PFT_DYN_SMEM
 #define PFT_DYN_SMEM(type, name) extern __shared__ type name[]
+#define PFT_DYN_SMEM_ALIGNED(type, name) extern __shared__ __align__(128) type name[]
 #endif
 
 namespace pft {
@@ -118,6 +119,16 @@ __device__ __forceinline__ double face_flux(const Consts &c, double pa, double p
 	return lam * (-ua + ub);
 }
 
+// a / b for b > 0.  A zero numerator (exact in the bulk of the domain: uniform temperature, p == 0
+// or 1) would send nvcc's IEEE division through its out-of-range slow path (~60 instructions);
+// (+-0)/b == +-0 for positive b, so return it directly.  Non-zero operands take the ordinary
+// correctly-rounded division.
+__device__ __forceinline__ double div_pos(double a, double b)
+{
+	if (a == 0.0) return a;
+	return a / b;
+}
+
 __device__ __forceinline__ double sshape(const Consts &c, double x)
 {
 	double y = x - c.p_eps0;
@@ -173,6 +184,48 @@ __device__ __forceinline__ void load_state(const StageArgs &a, long long idx, do
 }
 
 // ----------------------------------------------------------------------------------------
+
+// ---- stage 5 epilogue: grid-wide max of the error estimate, acceptance decision, host notification
+__device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, double emax, int nonfinite)
+{
+	// CTA max through a shared-memory atomic on the bit pattern (non-negative doubles order
+	// like their uint64 patterns; the tile need not be a multiple of the warp size)
+	__shared__ unsigned long long s_bits;
+	__shared__ int s_nonfinite;
+	if (tid == 0) { s_bits = 0ull; s_nonfinite = 0; }
+	__syncthreads();
+	if (emax > 0.0) atomicMax(&s_bits, (unsigned long long)__double_as_longlong(emax));
+	if (nonfinite) atomicOr(&s_nonfinite, 1);
+	__syncthreads();
+	if (tid == 0) {
+		Ctl *ctl = a.ctl;
+		if (s_bits) atomicMax(&ctl->eps_bits, s_bits);
+		if (s_nonfinite) atomicOr(&ctl->nonfinite, 1);
+		__threadfence();
+		unsigned int t = atomicAdd(&ctl->ticket, 1u);
+		if (t == a.nblocks - 1) {            // last CTA of the launch: every other CTA's max is in
+			__threadfence();
+			unsigned long long bits = atomicMax(&ctl->eps_bits, 0ull);
+			int nfl = atomicOr(&ctl->nonfinite, 0);
+			double eps = __longlong_as_double((long long)bits);
+			double ecmp = a.scale_eps ? eps * a.eps_scale : eps;            // RK_MPI_SAsolver_hybrid2.c:578
+			int acc = (ecmp < a.delta) || (a.h_abs < a.h_min);               // :599
+			if (a.handle_nan && nfl) acc = 0;                                 // :626-646
+			ctl->accept = acc;
+			ctl->eps_bits = 0ull;
+			ctl->nonfinite = 0;
+			ctl->ticket = 0u;
+			__threadfence();
+			HostSlot *s = a.slot;
+			s->eps = eps;
+			s->accept = acc;
+			s->nonfinite = nfl;
+			__threadfence_system();
+			*(volatile unsigned long long *)&s->seq = a.seq;
+			__threadfence_system();
+		}
+	}
+}
 
 // MODEL: 0 GradP (calc_mode 0/10), 1 SigmaP1-P (1/11), 2 temperature model (2)
 // HEAT : the heat equation is active (false for calc_mode 10/11: du/dt = 0, u is static)
@@ -290,7 +343,6 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 			const double unn = tu[cs + SP], gnn = tg[cs + SP];
 			double fe = face_flux(c, pc, pe, gc, ge, uc, ue);
 			double fn = face_flux(c, pc, pnn, gc, gnn, uc, unn);
-			double fzp = face_flux(c, pc, pn, gc, gn, uc, un);
 			double fw, fs;
 			if (FLUX) {
 				fxs[ty * (TX + 1) + tx + 1] = fe;
@@ -313,6 +365,9 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 				fw = face_flux(c, pw, pc, gw, gc, uw, uc);
 				fs = face_flux(c, ps, pc, gs, gc, us, uc);
 			}
+			// the z+ face is the first consumer of the plane fetched at the top of this iteration:
+			// keep it last so that the in-plane work covers the load latency
+			double fzp = face_flux(c, pc, pn, gc, gn, uc, un);
 			sum = c.h1_2 * (-fw + fe) + c.h2_2 * (-fs + fn) + c.h3_2 * (-fzm + fzp);   // equation.c:711-720
 			fzm = fzp;
 		}
@@ -324,7 +379,7 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 			double cp = mix3(pc, gc, c.g_cp, c.i_cp, c.w_cp);
 			double ch = cosh(c.gamma * (uc - c.u_star));
 			double dp_du = (-0.5 * c.gamma / (ch * ch)) * fmax(0.0, 1.0 - c.zeta * gc);
-			du = sum / (rho * (cp - c.L * dp_du));
+			du = div_pos(sum, rho * (cp - c.L * dp_du));
 			dp = dp_du * du;
 		} else {
 			// equation.c:659-694
@@ -341,12 +396,12 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 			} else {
 				dp += well - c.sam * sshape(c, pc) * sshape(c, one_m_p) * fmax(pc * one_m_p, 0.0) * du_star;   // :387
 			}
-			dp /= c.alpha;
+			dp = div_pos(dp, c.alpha);
 			dp *= fmax(0.0, 1.0 - c.zeta * gc);
 			if (HEAT) {
 				double rho = mix3(pc, gc, c.g_rho, c.i_rho, c.w_rho);
 				double cp = mix3(pc, gc, c.g_cp, c.i_cp, c.w_cp);
-				du = (sum / rho + c.L * dp) / cp;                                         // :711-723
+				du = div_pos(div_pos(sum, rho) + c.L * dp, cp);                           // :711-723
 			} else du = 0.0;
 		}
 
@@ -389,46 +444,7 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 		cur ^= 1;
 	}
 
-	// ---- stage 5: grid-wide max of the error estimate, acceptance decision, host notification
-	if (STAGE == 5) {
-		// CTA max through a shared-memory atomic on the bit pattern (non-negative doubles order
-		// like their uint64 patterns; the tile need not be a multiple of the warp size)
-		__shared__ unsigned long long s_bits;
-		__shared__ int s_nonfinite;
-		if (tid == 0) { s_bits = 0ull; s_nonfinite = 0; }
-		__syncthreads();
-		if (emax > 0.0) atomicMax(&s_bits, (unsigned long long)__double_as_longlong(emax));
-		if (nonfinite) atomicOr(&s_nonfinite, 1);
-		__syncthreads();
-		if (tid == 0) {
-			Ctl *ctl = a.ctl;
-			if (s_bits) atomicMax(&ctl->eps_bits, s_bits);
-			if (s_nonfinite) atomicOr(&ctl->nonfinite, 1);
-			__threadfence();
-			unsigned int t = atomicAdd(&ctl->ticket, 1u);
-			if (t == a.nblocks - 1) {            // last CTA of the launch: every other CTA's max is in
-				__threadfence();
-				unsigned long long bits = atomicMax(&ctl->eps_bits, 0ull);
-				int nfl = atomicOr(&ctl->nonfinite, 0);
-				double eps = __longlong_as_double((long long)bits);
-				double ecmp = a.scale_eps ? eps * a.eps_scale : eps;            // RK_MPI_SAsolver_hybrid2.c:578
-				int acc = (ecmp < a.delta) || (a.h_abs < a.h_min);               // :599
-				if (a.handle_nan && nfl) acc = 0;                                 // :626-646
-				ctl->accept = acc;
-				ctl->eps_bits = 0ull;
-				ctl->nonfinite = 0;
-				ctl->ticket = 0u;
-				__threadfence();
-				HostSlot *s = a.slot;
-				s->eps = eps;
-				s->accept = acc;
-				s->nonfinite = nfl;
-				__threadfence_system();
-				*(volatile unsigned long long *)&s->seq = a.seq;
-				__threadfence_system();
-			}
-		}
-	}
+	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -1,0 +1,340 @@
+// pft_kernels_tma.cuh -- the TMA-staged Merson stage kernel (sm_100a, float64, HEAT modes 0/1/2).
+//
+// Same arithmetic and the same five fused stages as `merson_stage` in pft_kernels.cuh (see the
+// header comment there for the reference citations); what changes is how HBM reaches the SM:
+//
+//   * every array a stage reads (x, K1, K3, K4 pairs or aux3, plus gl) has a 3-D tensor map over
+//     its (px, n2, n3+2) layout; ONE elected thread issues one `cp.async.bulk.tensor.3d` per array
+//     and z-plane, box = (TX+4) x (TY+2) x 1 (the inner start coordinate must be 16-byte aligned,
+//     measured on B200: an odd fp64 x-coordinate raises an illegal-instruction fault), so the tile arrives in shared memory together with
+//     its one-cell halo ring, without per-thread address arithmetic, without halo-duty loads and
+//     without holding in-flight loads in registers (SASS: UTMALDG);
+//   * three raw stage buffers rotate (plane k = centre, k+1 = being formed, k+2 = in flight);
+//     an mbarrier per buffer (expect_tx / complete_tx) tells the consumers when a plane landed,
+//     the CTA barrier that ends an iteration doubles as the "buffer free" signal;
+//   * the Merson stage input (x + h*sum a_i K_i) of plane k+1 is formed from the raw buffer right
+//     before plane k is computed: the centre value goes to the register window (z-1/z/z+1) and,
+//     with the ring cells, to a double-buffered state tile that plane k+1 will read its in-plane
+//     neighbours from; stages 1 and 3 read the raw buffer directly (their input is stored as is);
+//   * the operands of the output combination (x, K1, K3, K4 at the centre cell) are re-read from
+//     the raw buffer instead of being carried in registers across the iteration.
+//
+// Mirror boundaries: TMA zero-fills out-of-range box elements, so neighbour slots are clamped to
+// the domain instead (value-identical to the reference's mirrored ghost nodes).
+#pragma once
+#include "pft_kernels.cuh"
+
+#ifdef PFT_CUDA_EMU
+#include <cuda.h>           // tests/cuda_emu/cuda.h: emulated CUtensorMap
+#else
+#include <cuda.h>
+#endif
+
+namespace pft {
+
+constexpr int TMA_MAX_ARRAYS = 9;
+constexpr int TMA_STAGES = 3;
+
+struct alignas(64) TmaParams {
+	CUtensorMap maps[TMA_MAX_ARRAYS];   // order: p-type arrays, u-type arrays, gl (see stage_np)
+	Consts c;
+	Geom g;
+	StageArgs a;
+	int bx, by;                          // box extents: bx = TX+4 (TX even; the box starts at the even x = i0-2), by = TY+2
+	int as;                              // doubles per array buffer (bx*by rounded up to 16 = 128 B)
+};
+
+// number of p-type (and u-type) arrays stage S stages through shared memory
+__host__ __device__ constexpr int stage_np(int S) { return S == 1 ? 1 : S == 2 ? 2 : S == 3 ? 1 : S == 4 ? 3 : 4; }
+
+#ifndef PFT_CUDA_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"PFT_MBAR_WAIT:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra PFT_MBAR_DONE;\n"
+		"bra PFT_MBAR_WAIT;\n"
+		"PFT_MBAR_DONE:\n"
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+		::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+		: "memory");
+}
+#else
+// CPU emulation (tests/cuda_emu): a tensor load is a synchronous box copy with zero fill; an
+// mbarrier is a completed-phase counter
+inline void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
+inline void fence_mbar_init() {}
+inline void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) { *bar += ((uint64_t)bytes << 32); }
+inline void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	while ((uint32_t)(*bar & 1u) == parity) pft_emu::yield();
+}
+inline void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+	uint32_t n = pft_emu::tensor_load_3d(dst, map, x, y, z);
+	uint64_t pending = (*bar >> 32) - n;
+	uint64_t phase = *bar & 0xffffffffull;
+	if (pending == 0) phase += 1;
+	*bar = (pending << 32) | phase;
+}
+#endif
+
+// stage input from the raw values of one cell: r[0] = x (or aux3), r[1..] = K1, K3, K4
+template <int STAGE>
+__device__ __forceinline__ double form_state(const double *buf, int as, int slot, int first, double ha)
+{
+	const double *r = buf + first * as + slot;
+	if (STAGE == 1 || STAGE == 3) return r[0];
+	if (STAGE == 2) return r[as] * ha + r[0];                                               // hybrid2.c:388
+	if (STAGE == 4) return (r[as] + 3.0 * r[2 * as]) * ha + r[0];                           // :428
+	return (0.5 * r[as] - 1.5 * r[2 * as] + 2.0 * r[3 * as]) * ha + r[0];                   // :449
+}
+
+template <int STAGE, int MODEL, bool SHARE>
+__global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant__ TmaParams P)
+{
+	const Consts &c = P.c;
+	const Geom &g = P.g;
+	const StageArgs &a = P.a;
+
+	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) return; }
+
+	constexpr int NP = stage_np(STAGE);
+	constexpr int NA = 2 * NP + 1;
+	constexpr bool FORM = !(STAGE == 1 || STAGE == 3);
+	constexpr int IU = NP, IG = 2 * NP;          // first u-type array, the gl array
+
+	const int TX = blockDim.x, TY = blockDim.y;
+	const int tx = threadIdx.x, ty = threadIdx.y;
+	const int tid = ty * TX + tx;
+	const int BX = P.bx, AS = P.as;
+
+	PFT_DYN_SMEM_ALIGNED(double, smem_t);
+	double *raw = smem_t;                                            // [3][NA][AS]
+	double *tile = raw + TMA_STAGES * NA * AS;                       // [2][2][AS]   (FORM)
+	double *fxs = tile + (FORM ? 4 * AS : 0);                        // [TY][TX+1]   (SHARE)
+	double *fys = fxs + (SHARE ? TY * (TX + 1) : 0);                 // [TY+1][TX]   (SHARE)
+	__shared__ uint64_t full[TMA_STAGES];
+
+	const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+	const int i = i0 + tx, j = j0 + ty;
+	const bool active = (i < g.n1) && (j < g.n2);
+	const int cs = (ty + 1) * BX + (tx + 2);     // the box starts at x = i0-2: TMA needs a 16-byte aligned inner offset
+	// in-plane neighbour slots, clamped to the DOMAIN (zero-Neumann mirror, equation.c:142-160)
+	const int sW = (i > 0) ? cs - 1 : cs;
+	const int sE = (i < g.n1 - 1) ? cs + 1 : cs;
+	const int sS = (j > 0) ? cs - BX : cs;
+	const int sN = (j < g.n2 - 1) ? cs + BX : cs;
+
+	const int k0 = blockIdx.z * g.zc;
+	const int k1 = min(g.n3, k0 + g.zc);
+	// chunk-local plane index q: z = k0 - 1 + q, array plane index = k0 + q
+	const int qlo = (k0 == 0 && g.front) ? 1 : 0;                    // z-front mirror: plane -1 is never fetched
+	const int qhi = (k1 == g.n3 && g.rear) ? (k1 - k0) : (k1 - k0 + 1);   // z-rear ghost is Dirichlet/mirror
+
+	// ring duty (FORM stages): the first 2*TX+2*TY threads each form one ring cell per plane
+	const bool hduty = FORM && tid < 2 * TX + 2 * TY;
+	int hs = 0;
+	if (hduty) {
+		int hx, hy;
+		if (tid < TX) { hx = tid; hy = -1; }
+		else if (tid < 2 * TX) { hx = tid - TX; hy = TY; }
+		else if (tid < 2 * TX + TY) { hx = -1; hy = tid - 2 * TX; }
+		else { hx = TX; hy = tid - 2 * TX - TY; }
+		hs = (hy + 1) * BX + (hx + 2);
+	}
+	const bool fduty = SHARE && tid < TX + TY;
+
+	if (tid == 0) {
+		for (int b = 0; b < TMA_STAGES; b++) mbar_init(&full[b], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+
+	int next_q = qlo;            // thread 0: next plane to request
+	auto issue_upto = [&](int qmax) {
+		while (next_q <= qhi && next_q <= qmax) {
+			const int b = next_q % TMA_STAGES;
+			mbar_arrive_expect_tx(&full[b], (uint32_t)(NA * BX * P.by * sizeof(double)));
+			#pragma unroll
+			for (int m = 0; m < NA; m++)
+				tma_load_3d(raw + (b * NA + m) * AS, &P.maps[m], i0 - 2, j0 - 1, k0 + next_q, &full[b]);
+			next_q++;
+		}
+	};
+	if (tid == 0) issue_upto(qlo + TMA_STAGES - 1);
+
+	uint32_t phase_bits = 0;     // per-buffer parity of the next completion to wait for
+	auto wait_plane = [&](int q) {
+		const int b = q % TMA_STAGES;
+		mbar_wait(&full[b], (phase_bits >> b) & 1u);
+		phase_bits ^= (1u << b);
+	};
+
+	double um, pm, gm, uc, pc, gc, un, pn, gn;
+	double fzm = 0.0, emax = 0.0;
+	int nonfinite = 0;
+
+	// ---- prologue
+	if (qlo == 0) {
+		wait_plane(0);
+		const double *rb = raw;
+		pm = form_state<STAGE>(rb, AS, cs, 0, a.ha);
+		um = form_state<STAGE>(rb, AS, cs, IU, a.ha);
+		gm = rb[IG * AS + cs];
+	}
+	{
+		wait_plane(1);
+		const double *rb = raw + (1 % TMA_STAGES) * NA * AS;
+		pc = form_state<STAGE>(rb, AS, cs, 0, a.ha);
+		uc = form_state<STAGE>(rb, AS, cs, IU, a.ha);
+		gc = rb[IG * AS + cs];
+		if (FORM) {
+			tile[cs] = pc; tile[AS + cs] = uc;
+			if (hduty) { tile[hs] = form_state<STAGE>(rb, AS, hs, 0, a.ha); tile[AS + hs] = form_state<STAGE>(rb, AS, hs, IU, a.ha); }
+		}
+		if (qlo == 1) { um = uc; pm = pc; gm = gc; }                  // equation.c:164-174
+		fzm = face_flux(c, pm, pc, gm, gc, um, uc);
+	}
+	__syncthreads();
+
+	int cur = 0;
+	for (int k = k0; k < k1; ++k) {
+		const int q = k - k0 + 1;
+		const bool more = (k + 1 < k1);
+		const double *rb = raw + (q % TMA_STAGES) * NA * AS;         // raw planes of the centre plane k
+		const double *rg = rb + IG * AS;
+
+		if (tid == 0) issue_upto(q + 2);      // its buffer held plane q-1, released by the barrier below
+
+		// ---- plane k+1: form the stage input (centre -> registers, centre + ring -> the other tile)
+		if (q + 1 <= qhi) {
+			wait_plane(q + 1);
+			const double *rn = raw + ((q + 1) % TMA_STAGES) * NA * AS;
+			pn = form_state<STAGE>(rn, AS, cs, 0, a.ha);
+			un = form_state<STAGE>(rn, AS, cs, IU, a.ha);
+			gn = rn[IG * AS + cs];
+			if (FORM && more) {
+				double *tn = tile + (cur ^ 1) * 2 * AS;
+				tn[cs] = pn; tn[AS + cs] = un;
+				if (hduty) { tn[hs] = form_state<STAGE>(rn, AS, hs, 0, a.ha); tn[AS + hs] = form_state<STAGE>(rn, AS, hs, IU, a.ha); }
+			}
+		} else {
+			un = a.dir_u; pn = pc; gn = gc;                             // equation.c:175-183 / :251-261
+		}
+
+		// ---- plane k
+		const double *tp = FORM ? tile + cur * 2 * AS : rb;
+		const double *tu = FORM ? tp + AS : rb + IU * AS;
+		const double pw = tp[sW], pe = tp[sE], ps = tp[sS], pnn = tp[sN];
+
+		double sum;
+		{
+			const double ue = tu[sE], ge = rg[sE];
+			const double unn = tu[sN], gnn = rg[sN];
+			double fe = face_flux(c, pc, pe, gc, ge, uc, ue);
+			double fn = face_flux(c, pc, pnn, gc, gnn, uc, unn);
+			double fw, fs;
+			if (SHARE) {
+				fxs[ty * (TX + 1) + tx + 1] = fe;
+				fys[(ty + 1) * TX + tx] = fn;
+				if (fduty) {
+					if (tid < TY) {           // west boundary face of tile row `tid`
+						const int s1 = (tid + 1) * BX + 2;
+						const int s0 = (i0 > 0) ? s1 - 1 : s1;
+						fxs[tid * (TX + 1)] = face_flux(c, tp[s0], tp[s1], rg[s0], rg[s1], tu[s0], tu[s1]);
+					} else {                  // south boundary face of tile column `tid-TY`
+						const int s1 = BX + (tid - TY) + 2;
+						const int s0 = (j0 > 0) ? s1 - BX : s1;
+						fys[tid - TY] = face_flux(c, tp[s0], tp[s1], rg[s0], rg[s1], tu[s0], tu[s1]);
+					}
+				}
+				__syncthreads();
+				fw = fxs[ty * (TX + 1) + tx];
+				fs = fys[ty * TX + tx];
+			} else {
+				fw = face_flux(c, pw, pc, rg[sW], gc, tu[sW], uc);
+				fs = face_flux(c, ps, pc, rg[sS], gc, tu[sS], uc);
+			}
+			double fzp = face_flux(c, pc, pn, gc, gn, uc, un);
+			sum = c.h1_2 * (-fw + fe) + c.h2_2 * (-fs + fn) + c.h3_2 * (-fzm + fzp);   // equation.c:711-720
+			fzm = fzp;
+		}
+
+		double du, dp;
+		const double rho = mix3(pc, gc, c.g_rho, c.i_rho, c.w_rho);
+		const double cp = mix3(pc, gc, c.g_cp, c.i_cp, c.w_cp);
+		if (MODEL == 2) {
+			double ch = cosh(c.gamma * (uc - c.u_star));                                   // equation.c:835-867
+			double dp_du = (-0.5 * c.gamma / (ch * ch)) * fmax(0.0, 1.0 - c.zeta * gc);
+			du = div_pos(sum, rho * (cp - c.L * dp_du));
+			dp = dp_du * du;
+		} else {
+			dp = c.h1_2 * (-(-pw + pc) + (-pc + pe))                                       // equation.c:659-669
+			   + c.h2_2 * (-(-ps + pc) + (-pc + pnn))
+			   + c.h3_2 * (-(-pm + pc) + (-pc + pn));
+			double one_m_p = 1.0 - pc;
+			double well = c.xi_2_inv_a * pc * one_m_p * (pc - 0.5);
+			double du_star = uc - c.u_star;
+			if (MODEL == 0) {
+				double gx = c.h1_d2 * (-pw + pe), gy = c.h2_d2 * (-ps + pnn), gz = c.h3_d2 * (-pm + pn);
+				double nrm = sqrt(gx * gx + gy * gy + gz * gz) + 1E-10;                   // :332-336
+				dp += well - c.bam * nrm * du_star;                                           // :370
+			} else {
+				dp += well - c.sam * sshape(c, pc) * sshape(c, one_m_p) * fmax(pc * one_m_p, 0.0) * du_star;   // :387
+			}
+			dp = div_pos(dp, c.alpha);
+			dp *= fmax(0.0, 1.0 - c.zeta * gc);
+			du = div_pos(div_pos(sum, rho) + c.L * dp, cp);                                   // :711-723
+		}
+
+		// ---- fused combination that follows this stage (operands re-read from the raw buffer)
+		if (active) {
+			const long long o = (long long)(k + 1) * g.plane + (long long)j * g.px + i;
+			if (STAGE == 1 || STAGE == 3 || STAGE == 4) {
+				a.op[o] = dp;
+				a.ou[o] = du;
+			} else if (STAGE == 2) {
+				a.op[o] = (rb[AS + cs] + dp) * a.hb + rb[cs];                               // hybrid2.c:408
+				a.ou[o] = (rb[(IU + 1) * AS + cs] + du) * a.hb + rb[IU * AS + cs];
+			} else {
+				const double xp = rb[cs], k1p = rb[AS + cs], k3p = rb[2 * AS + cs], k4p = rb[3 * AS + cs];
+				const double xu = rb[IU * AS + cs], k1u = rb[(IU + 1) * AS + cs], k3u = rb[(IU + 2) * AS + cs], k4u = rb[(IU + 3) * AS + cs];
+				double e = fabs(0.2 * k1p - 0.9 * k3p + 0.8 * k4p - 0.1 * dp);              // :521
+				double eu = fabs(0.2 * k1u - 0.9 * k3u + 0.8 * k4u - 0.1 * du);
+				if (!(e <= 1.7976931348623157e308) || !(eu <= 1.7976931348623157e308)) nonfinite = 1;
+				emax = (e > emax) ? e : emax;
+				emax = (eu > emax) ? eu : emax;
+				a.op[o] = xp + a.hb * (0.5 * (k1p + dp) + 2.0 * k4p);                       // :667
+				a.ou[o] = xu + a.hb * (0.5 * (k1u + du) + 2.0 * k4u);
+			}
+		}
+
+		__syncthreads();        // tile[cur^1] complete; raw buffer of plane k-1.. free for thread 0
+		um = uc; pm = pc; gm = gc;
+		uc = un; pc = pn; gc = gn;
+		cur ^= 1;
+	}
+
+	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
+}
+
+}  // namespace pft

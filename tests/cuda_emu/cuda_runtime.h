@@ -35,6 +35,9 @@ extern dim3 g_blockDim, g_gridDim;
 extern unsigned char *g_dyn_smem;
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body);
 void syncthreads();
+void yield();                        // let the other fibers of the CTA run (spin-wait loops)
+struct CUtensorMap_fwd;
+uint32_t tensor_load_3d(void *dst, const void *map, int x, int y, int z);   // returns the bytes written
 }
 
 #define threadIdx (pft_emu::g_threadIdx)
@@ -50,6 +53,7 @@ void syncthreads();
 #define __grid_constant__
 #define __shared__ static
 #define PFT_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(pft_emu::g_dyn_smem)
+#define PFT_DYN_SMEM_ALIGNED(type, name) type *name = reinterpret_cast<type *>(pft_emu::g_dyn_smem)
 
 static inline void __syncthreads() { pft_emu::syncthreads(); }
 static inline void __threadfence() {}
@@ -101,3 +105,7 @@ template <class T> static inline cudaError_t cudaHostGetDevicePointer(T **d, voi
 static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+enum { cudaEnableDefault = 0 };
+typedef int cudaDriverEntryPointQueryResult;
+enum { cudaDriverEntryPointSuccess = 0 };
+cudaError_t cudaGetDriverEntryPoint(const char *symbol, void **fn, unsigned long long flags, cudaDriverEntryPointQueryResult *st);

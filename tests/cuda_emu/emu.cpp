@@ -2,6 +2,7 @@
 // One CTA at a time; one ucontext fiber per CUDA thread; __syncthreads yields to the scheduler,
 // which resumes the fibers once every live fiber of the CTA has arrived.
 #include "cuda_runtime.h"
+#include "cuda.h"
 #include <ucontext.h>
 #include <stdio.h>
 #include <vector>
@@ -36,13 +37,37 @@ void syncthreads()
 	swapcontext(&fibers[cur].ctx, &sched_ctx);
 }
 
+void yield()
+{
+	swapcontext(&fibers[cur].ctx, &sched_ctx);      // stays READY
+}
+
+uint32_t tensor_load_3d(void *dst, const void *map_, int x, int y, int z)
+{
+	const CUtensorMap *m = (const CUtensorMap *)map_;
+	double *d = (double *)dst;
+	if ((x * 8) & 15) { fprintf(stderr, "cuda_emu: TMA inner coordinate %d is not 16-byte aligned (B200 raises an illegal-instruction fault)\n", x); abort(); }
+	if ((uintptr_t)dst & 127) { fprintf(stderr, "cuda_emu: TMA shared-memory destination is not 128-byte aligned\n"); abort(); }
+	const char *base = (const char *)m->base;
+	for (uint32_t bz = 0; bz < m->box[2]; bz++)
+		for (uint32_t by = 0; by < m->box[1]; by++)
+			for (uint32_t bx = 0; bx < m->box[0]; bx++) {
+				long long gx = (long long)x + bx, gy = (long long)y + by, gz = (long long)z + bz;
+				double v = 0.0;
+				if (gx >= 0 && gy >= 0 && gz >= 0 && gx < (long long)m->dim[0] && gy < (long long)m->dim[1] && gz < (long long)m->dim[2])
+					v = *(const double *)(base + gz * (long long)m->stride[1] + gy * (long long)m->stride[0] + gx * 8);
+				d[((size_t)bz * m->box[1] + by) * m->box[0] + bx] = v;
+			}
+	return m->box[0] * m->box[1] * m->box[2] * 8u;
+}
+
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body)
 {
 	const int nt = (int)(block.x * block.y * block.z);
 	if ((int)fibers.size() < nt) fibers.resize(nt);
 	if (stacks.size() < (size_t)nt * STACK) stacks.resize((size_t)nt * STACK);
-	if (smem_buf.size() < smem_bytes + 64) smem_buf.resize(smem_bytes + 64);
-	g_dyn_smem = smem_buf.data();
+	if (smem_buf.size() < smem_bytes + 256) smem_buf.resize(smem_bytes + 256);
+	g_dyn_smem = (unsigned char *)(((uintptr_t)smem_buf.data() + 127) & ~(uintptr_t)127);
 	g_blockDim = block; g_gridDim = grid;
 	cur_body = &body;
 	for (unsigned bz = 0; bz < grid.z; bz++)
@@ -79,3 +104,24 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 }
 
 }  // namespace pft_emu
+
+CUresult cuTensorMapEncodeTiled(CUtensorMap *m, CUtensorMapDataType, cuuint32_t rank, void *addr, const cuuint64_t *dim,
+                                const cuuint64_t *strides, const cuuint32_t *box, const cuuint32_t *,
+                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill)
+{
+	if (rank != 3) return 1;
+	if (((uintptr_t)addr & 15) || (strides[0] & 15) || (strides[1] & 15) || ((box[0] * 8) & 15) || box[0] > 256 || box[1] > 256) return 1;   // the real constraints
+	memset(m, 0, sizeof *m);
+	m->base = addr;
+	for (int i = 0; i < 3; i++) { m->dim[i] = dim[i]; m->box[i] = box[i]; }
+	m->stride[0] = strides[0]; m->stride[1] = strides[1];
+	return CUDA_SUCCESS;
+}
+
+cudaError_t cudaGetDriverEntryPoint(const char *symbol, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *st)
+{
+	*fn = nullptr;
+	if (!strcmp(symbol, "cuTensorMapEncodeTiled")) *fn = (void *)cuTensorMapEncodeTiled;
+	if (st) *st = *fn ? cudaDriverEntryPointSuccess : 1;
+	return *fn ? cudaSuccess : 1;
+}

@@ -19,7 +19,7 @@ from bench import make_spec, STAGE_BYTES_HEAT, STAGE_BYTES_NOHEAT  # noqa: E402
 
 
 def run(spec, fields, env, flags, attempts, t_h):
-    for k in ("PFT_TX", "PFT_TY", "PFT_ZCHUNKS", "PFT_THREADS", "PFT_PROFILE_STAGES"):
+    for k in ("PFT_TX", "PFT_TY", "PFT_ZCHUNKS", "PFT_THREADS", "PFT_PROFILE_STAGES", "PFT_LEGACY"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     sol = SlabSolver(spec, flags=flags)
@@ -63,17 +63,20 @@ def main():
     fields = s0.download_interior()
     t_h = (s0.sys.t, s0.sys.h)
     s0.close()
-    configs = [({}, 0), ({}, 1), ({"PFT_PROFILE_STAGES": 1}, 0), ({"PFT_PROFILE_STAGES": 1}, 1), ({}, 2)]
-    tiles = [(100, 5), (50, 10), (40, 12), (25, 20), (50, 5), (40, 6), (100, 4), (100, 3), (64, 8), (32, 16), (50, 8), (50, 6)]
+    P = {"PFT_PROFILE_STAGES": 1}
+    configs = [({}, 0), ({}, 1), (dict(P), 0), (dict(P), 1), ({"PFT_LEGACY": 1}, 0), ({"PFT_LEGACY": 1}, 1)]
+    tiles = [(100, 5), (50, 10), (50, 5), (50, 4), (50, 3), (100, 2), (100, 3), (40, 6), (25, 10), (20, 12), (50, 8), (200, 2)]
     if args.quick:
-        tiles = tiles[:4]
+        tiles = tiles[:6]
     for tx, ty in tiles:
         if tx > spec.n1:
             continue
-        configs.append(({"PFT_TX": tx, "PFT_TY": ty}, 0))
-    for tx, ty in ((50, 10), (100, 5), (50, 5)):
-        for zc in (1, 2, 4, 8, 16, 37, 74):
-            configs.append(({"PFT_TX": tx, "PFT_TY": ty, "PFT_ZCHUNKS": zc}, 0))
+        for fl in (0, 1):
+            configs.append(({"PFT_TX": tx, "PFT_TY": ty}, fl))
+    if not args.quick:
+        for tx, ty in ((50, 10), (50, 5)):
+            for zc in (4, 8, 16, 37, 74):
+                configs.append(({"PFT_TX": tx, "PFT_TY": ty, "PFT_ZCHUNKS": zc}, 0))
     for env, flags in configs:
         try:
             print(json.dumps(run(spec, fields, env, flags, args.attempts, t_h)), flush=True)
