@@ -56,10 +56,11 @@ extern "C" {
 #define PFT_SOLVE_NAN        (-4)  /* RK_MPI_SA_solve: -4 */
 
 /* flags for pft_create */
-#define PFT_FLAG_NO_FLUX_SHARING  1u   /* every cell recomputes its six face fluxes (debug / A-B) */
+#define PFT_FLAG_NO_FLUX_SHARING  1u   /* every cell computes its six face fluxes itself (the default) */
 #define PFT_FLAG_NO_SPECULATION   2u   /* do not launch the next K1 before the step-size decision */
 #define PFT_FLAG_RECOMPUTE_K1     4u   /* recompute K1 after a rejected attempt, like the reference */
 #define PFT_FLAG_LEGACY_LOADS     8u   /* per-thread global loads instead of TMA tile staging (debug / A-B) */
+#define PFT_FLAG_FLUX_SHARING    16u   /* cells exchange face fluxes through shared memory (A-B; costs a second CTA barrier) */
 
 typedef struct pft_solver pft_solver;
 

@@ -190,28 +190,34 @@ static int env_int(const char *name, int dflt)
 
 static void choose_tile(int n1, int n2, int max_threads, int *TX, int *TY)
 {
+	// Cost model fitted to the B200 sweep in profiles/round1_tuning.md: wasted threads of ragged
+	// tiles, the halo ring the TMA box drags along ((TX+4) x (TY+2) for TX x TY cells), and a
+	// penalty for short box rows (a 26-wide tile measured 15% slower than a 50-wide one with the
+	// same thread count).
 	double best = 1e300;
 	int btx = std::min(n1, 64), bty = std::max(3, std::min(n2, max_threads / std::max(1, btx)));
 	for (int nx = 1; nx <= 64; nx++) {
 		int tx = (n1 + nx - 1) / nx;
+		tx += tx & 1;                         // tile origins must be even (TMA inner-offset alignment)
 		if (tx > 128) continue;
 		if (tx < 8 && nx > 1) break;
 		for (int ty = std::min(n2, max_threads / tx); ty >= 3; ty--) {
 			if (tx * ty < 2 * tx + 2 * ty) continue;
-			if (tx * ty < std::min(128, n1 * n2)) break;
+			if (tx * ty < std::min(96, n1 * n2)) break;
 			double tiles = (double)((n1 + tx - 1) / tx) * ((n2 + ty - 1) / ty);
 			double waste = tiles * tx * ty / ((double)n1 * n2);
-			// ring traffic in 32-byte sectors relative to the tile's own sectors
-			double ring = (2.0 * tx * 8 + (nx > 1 ? 2.0 * ty * 32 : 0.0)) / (tx * ty * 8.0);
-			double small = (tx * ty < 384) ? 1.0 + 0.15 * (384 - tx * ty) / 384.0 : 1.0;
-			double cost = waste * (1.0 + 0.5 * ring) * small;
+			double box = (double)(tx + 4) * (ty + 2) / ((double)tx * ty);
+			double rows = 1.0 + 24.0 / tx;
+			double small = (tx * ty < 192) ? 1.0 + 0.2 * (192 - tx * ty) / 192.0 : 1.0;
+			double flat = (ty < 5) ? 1.0 + 0.06 * (5 - ty) : 1.0;     // 3-4 row tiles measured slower
+			double cost = waste * (0.6 + 0.4 * box) * rows * small * flat;
 			if (cost < best) { best = cost; btx = tx; bty = ty; }
 		}
 	}
 	// degenerate grids (a single row or column): pad the tile with inactive threads so that the
 	// halo-ring duty (2*TX+2*TY cells) still fits into the CTA
 	if (btx < 4) btx = 4;
-	if (bty < 4) bty = 4;
+	if (btx * bty < 2 * btx + 2 * bty) bty = 4;
 	*TX = btx; *TY = bty;
 }
 
@@ -504,7 +510,9 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	s->device = device;
 	s->model = (cs->calc_mode == 2) ? 2 : (cs->calc_mode % 10);
 	s->heat = !(cs->calc_mode == 10 || cs->calc_mode == 11);
-	s->share = s->heat && !(flags & PFT_FLAG_NO_FLUX_SHARING) && !env_int("PFT_NO_SHARE", 0);
+	// Sharing face fluxes through shared memory saves ~25% of the fp64 work but costs a second CTA
+	// barrier per plane; measured on B200 it loses (profiles/round1_tuning.md), so it is opt-in.
+	s->share = s->heat && !(flags & PFT_FLAG_NO_FLUX_SHARING) && ((flags & PFT_FLAG_FLUX_SHARING) || env_int("PFT_SHARE", 0));
 	s->speculate = !(flags & PFT_FLAG_NO_SPECULATION) && !env_int("PFT_NO_SPECULATION", 0) && cs->nranks == 1;
 	s->profile = env_int("PFT_PROFILE_STAGES", 0) != 0;
 	make_consts(s);
@@ -519,7 +527,7 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	s->N1 = cs->n1 + 2 * PFT_BT; s->N2 = cs->n2 + 2 * PFT_BT; s->N3 = cs->n3 + 2 * PFT_BT;
 	s->padded = (long long)PFT_NVAR * s->N1 * s->N2 * s->N3;
 
-	int max_threads = env_int("PFT_THREADS", 512);
+	int max_threads = env_int("PFT_THREADS", 256);     // two or three CTAs per SM overlap each other's barrier waits
 	if (max_threads < 64) max_threads = 64;
 	if (max_threads > 512) max_threads = 512;
 	choose_tile(cs->n1, cs->n2, max_threads, &s->TX, &s->TY);

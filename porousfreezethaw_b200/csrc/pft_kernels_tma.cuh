@@ -217,18 +217,20 @@ __global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant
 	__syncthreads();
 
 	int cur = 0;
+	int bq = 1, bn = 2;          // raw buffers of plane q (centre) and q+1; (q+2) % 3 == the third one
 	for (int k = k0; k < k1; ++k) {
 		const int q = k - k0 + 1;
 		const bool more = (k + 1 < k1);
-		const double *rb = raw + (q % TMA_STAGES) * NA * AS;         // raw planes of the centre plane k
+		const double *rb = raw + bq * NA * AS;                        // raw planes of the centre plane k
 		const double *rg = rb + IG * AS;
 
 		if (tid == 0) issue_upto(q + 2);      // its buffer held plane q-1, released by the barrier below
 
 		// ---- plane k+1: form the stage input (centre -> registers, centre + ring -> the other tile)
 		if (q + 1 <= qhi) {
-			wait_plane(q + 1);
-			const double *rn = raw + ((q + 1) % TMA_STAGES) * NA * AS;
+			mbar_wait(&full[bn], (phase_bits >> bn) & 1u);
+			phase_bits ^= (1u << bn);
+			const double *rn = raw + bn * NA * AS;
 			pn = form_state<STAGE>(rn, AS, cs, 0, a.ha);
 			un = form_state<STAGE>(rn, AS, cs, IU, a.ha);
 			gn = rn[IG * AS + cs];
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant
 		um = uc; pm = pc; gm = gc;
 		uc = un; pc = pn; gc = gn;
 		cur ^= 1;
+		{ const int b3 = 3 - bq - bn; bq = bn; bn = b3; }
 	}
 
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);

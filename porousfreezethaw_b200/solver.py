@@ -23,6 +23,8 @@ NVAR = 3
 FLAG_NO_FLUX_SHARING = 1
 FLAG_NO_SPECULATION = 2
 FLAG_RECOMPUTE_K1 = 4
+FLAG_LEGACY_LOADS = 8
+FLAG_FLUX_SHARING = 16
 
 SOLVE_DONE, SOLVE_INTERRUPTED, SOLVE_BUDGET = 0, 1, 2
 

@@ -13,7 +13,8 @@ import pytest
 import parity
 from oracle import pyoracle as po
 from porousfreezethaw_b200 import cases
-from porousfreezethaw_b200.solver import SlabSolver, FLAG_NO_FLUX_SHARING, FLAG_NO_SPECULATION, FLAG_RECOMPUTE_K1
+from porousfreezethaw_b200.solver import (SlabSolver, FLAG_NO_FLUX_SHARING, FLAG_NO_SPECULATION, FLAG_RECOMPUTE_K1,
+                                          FLAG_LEGACY_LOADS, FLAG_FLUX_SHARING)
 
 pytestmark = pytest.mark.gpu
 
@@ -36,7 +37,8 @@ def test_rhs_mode2_tolerance(gpu_lib):
     parity.check_rhs(cases.small_case(24, 20, 32, calc_mode=2), gpu_lib, exact=False)
 
 
-@pytest.mark.parametrize("mode,flags", [(0, 0), (0, FLAG_NO_FLUX_SHARING), (1, 0), (10, 0), (11, 0)])
+@pytest.mark.parametrize("mode,flags", [(0, 0), (0, FLAG_FLUX_SHARING), (0, FLAG_LEGACY_LOADS), (0, FLAG_LEGACY_LOADS | FLAG_FLUX_SHARING),
+                                        (1, 0), (1, FLAG_FLUX_SHARING), (10, 0), (11, 0)])
 def test_fused_stages_bit_exact(gpu_lib, mode, flags):
     parity.check_fused_stages(cases.small_case(24, 20, 32, calc_mode=mode), gpu_lib, flags=flags)
 
@@ -74,7 +76,7 @@ def test_adaptive_sequence_bit_exact(gpu_lib, mode):
     parity.check_adaptive(cases.small_case(24, 20, 32, calc_mode=mode), gpu_lib, T=60.0, chunks=3, with_service=True)
 
 
-@pytest.mark.parametrize("flags", [FLAG_NO_SPECULATION, FLAG_RECOMPUTE_K1, FLAG_NO_FLUX_SHARING | FLAG_NO_SPECULATION])
+@pytest.mark.parametrize("flags", [FLAG_NO_SPECULATION, FLAG_RECOMPUTE_K1, FLAG_FLUX_SHARING | FLAG_NO_SPECULATION, FLAG_LEGACY_LOADS])
 def test_adaptive_variants(gpu_lib, flags):
     parity.check_adaptive(cases.small_case(24, 20, 32, calc_mode=0), gpu_lib, T=40.0, chunks=2, flags=flags)
 
@@ -187,7 +189,8 @@ def hr_state(gpu_lib):
 @pytest.mark.parametrize("env,flags", [
     ({"PFT_TX": "40", "PFT_TY": "12", "PFT_ZCHUNKS": "7"}, 0),
     ({"PFT_TX": "100", "PFT_TY": "5", "PFT_ZCHUNKS": "1"}, 0),
-    ({}, FLAG_NO_FLUX_SHARING),
+    ({}, FLAG_FLUX_SHARING),
+    ({}, FLAG_LEGACY_LOADS),
     ({}, FLAG_RECOMPUTE_K1 | FLAG_NO_SPECULATION),
 ])
 def test_fullsize_invariance(gpu_lib, hr_state, monkeypatch, env, flags):

@@ -64,14 +64,14 @@ def main():
     t_h = (s0.sys.t, s0.sys.h)
     s0.close()
     P = {"PFT_PROFILE_STAGES": 1}
-    configs = [({}, 0), ({}, 1), (dict(P), 0), (dict(P), 1), ({"PFT_LEGACY": 1}, 0), ({"PFT_LEGACY": 1}, 1)]
-    tiles = [(100, 5), (50, 10), (50, 5), (50, 4), (50, 3), (100, 2), (100, 3), (40, 6), (25, 10), (20, 12), (50, 8), (200, 2)]
+    configs = [({}, 0), ({}, 16), (dict(P), 0), (dict(P), 16), ({"PFT_LEGACY": 1}, 0), ({"PFT_LEGACY": 1}, 16)]
+    tiles = [(100, 5), (50, 10), (50, 5), (50, 4), (50, 3), (100, 3), (40, 6), (26, 10), (20, 12), (50, 8), (50, 6), (100, 4)]
     if args.quick:
         tiles = tiles[:6]
     for tx, ty in tiles:
         if tx > spec.n1:
             continue
-        for fl in (0, 1):
+        for fl in (0, 16):
             configs.append(({"PFT_TX": tx, "PFT_TY": ty}, fl))
     if not args.quick:
         for tx, ty in ((50, 10), (50, 5)):
