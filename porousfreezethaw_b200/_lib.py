@@ -64,7 +64,7 @@ def load(path: str | None = None) -> C.CDLL:
             f"{path} not found: the sm_100a CUDA library has not been built "
             f"(run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C porousfreezethaw_b200/csrc`). "
             f"porousfreezethaw_b200 has no CPU fallback.")
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path)
     vp = C.c_void_p
     lib.pft_last_error.restype = C.c_char_p
     lib.pft_version.restype = C.c_char_p

@@ -1,0 +1,73 @@
+"""Host-side logic that needs neither GPU nor reference: slab partition, case tables, the
+reference-shaped solver-module entry points of the C drop-in (argument checking, return codes)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from porousfreezethaw_b200 import _lib, cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("total,nranks", [(400, 1), (400, 8), (100, 3), (101, 4), (7, 7), (50, 6)])
+def test_partition_matches_reference_rule(total, nranks):
+    """intertrack.c:1780-1787: contiguous slabs, remainder rows one each to the lowest ranks"""
+    lib = po.load_oracle()
+    row = 0
+    for r in range(nranks):
+        n3, first = cases.partition(total, nranks, r)
+        a, b = C.c_int(), C.c_int()
+        lib.pfo_partition(total, nranks, r, C.byref(a), C.byref(b))
+        assert (n3, first) == (a.value, b.value) == po.partition(total, nranks, r)
+        assert first == row and n3 in (total // nranks, total // nranks + 1)
+        row += n3
+    assert row == total
+
+
+def test_archived_case_tables():
+    for name, grid in (("100-GradP", (50, 50, 100)), ("200-GradP", (100, 100, 200)), ("400-SigmaP1-P-smallsigma", (200, 200, 400))):
+        cs = cases.archived_case(name)
+        assert (cs.n1, cs.n2, cs.n3) == grid and cs.cells == grid[0] * grid[1] * grid[2]
+        p = cs.params
+        assert p["alpha"] == 997.0 * 4.18e3 * (3 if "smallsigma" in name else 1)
+        assert p["xi"] == 0.06 / (grid[2] / 1) * 1.0 if False else p["xi"] == 0.06 / grid[2]
+        assert p["top_temp1"] == 273.15 - 25 and p["phase_switch_time"] == 5 * 3600.0
+        assert cs.snapshot_time(1) == pytest.approx(36000.0 / 99)
+    assert len(cases.PARAM_NAMES) == _lib.NPARAM == po.NPARAM and cases.PARAM_NAMES == po.PARAM_NAMES
+
+
+def test_solver_module_return_codes():
+    """RK_MPI_SA_init / cleanup / check_mem follow RK_MPI_SAsolver_hybrid2.c:72-212"""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "porousfreezethaw_b200", "csrc"), "all"], check=True, stdout=subprocess.DEVNULL)
+    rk = C.CDLL(_lib.RK_LIB_PATH)
+
+    class MemDist(C.Structure):
+        _fields_ = [("n_chunks", C.c_int), ("chunk_start", C.POINTER(C.c_int)), ("chunk_size", C.POINTER(C.c_int)),
+                    ("chunk_eps_mult", C.POINTER(C.c_double))]
+
+    def dist(starts, sizes):
+        n = len(starts)
+        a, b, m = (C.c_int * n)(*starts), (C.c_int * n)(*sizes), (C.c_double * n)(*([1.0] * n))
+        d = MemDist(n, a, b, m)
+        d._keep = (a, b, m)
+        return d
+
+    assert rk.RK_MPI_SA_cleanup() == -3
+    assert rk.RK_MPI_SA_check_mem(C.byref(dist([0], [4]))) == -3
+    assert rk.RK_MPI_SA_init(0, 0, 0) == -2
+    assert rk.RK_MPI_SA_init(100, 0, 0) == 0
+    assert rk.RK_MPI_SA_init(100, 0, 0) == -3
+    assert rk.RK_MPI_SA_check_mem(C.byref(dist([0, 10, 20], [5, 10, 30]))) == 0
+    assert rk.RK_MPI_SA_check_mem(C.byref(dist([0, 10, 20], [5, 10, 81]))) == -5
+    assert rk.RK_MPI_SA_check_mem(C.byref(dist([0, 4], [5, 10]))) == -6
+    assert rk.RK_MPI_SA_check_mem(C.byref(dist([0, 10], [5, 0]))) == -6
+    d0 = dist([0], [1]); d0.n_chunks = 0
+    assert rk.RK_MPI_SA_check_mem(C.byref(d0)) == -7
+    assert rk.RK_MPI_SA_solve(C.c_double(1.0), None) == -2
+    rk.RK_MPI_SA_handle_NAN(5)
+    assert rk.RK_MPI_SA_check_NAN() == 0
+    assert rk.RK_MPI_SA_cleanup() == 0
