@@ -168,6 +168,7 @@ struct pft_solver {
 	pft_stats st;
 	// TMA path (heat modes): one tensor map per array, box = tile + halo ring
 	bool use_tma;
+	bool split;           // split-phase mbarriers instead of a CTA barrier per plane
 	CUtensorMap tmap[A_COUNT][2];
 	CUtensorMap tmap_gl;
 	int bx, by, as;
@@ -321,10 +322,10 @@ static cudaError_t launch_stage_t(pft_solver *s, const KParams &kp)
 	return launch_t<STAGE, 1, false, false>(s, kp);
 }
 
-template <int STAGE, int MODEL, bool SHARE>
+template <int STAGE, int MODEL, bool SHARE, bool SPLIT>
 static cudaError_t launch_tma_t(pft_solver *s, const TmaParams &kp)
 {
-	auto fn = merson_stage_tma<STAGE, MODEL, SHARE>;
+	auto fn = merson_stage_tma<STAGE, MODEL, SHARE, SPLIT>;
 	static bool attr_set = false;
 	if (!attr_set) {
 		cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
@@ -338,9 +339,14 @@ static cudaError_t launch_tma_t(pft_solver *s, const TmaParams &kp)
 template <int STAGE>
 static cudaError_t launch_stage_tma_t(pft_solver *s, const TmaParams &kp)
 {
-	if (s->model == 2) return s->share ? launch_tma_t<STAGE, 2, true>(s, kp) : launch_tma_t<STAGE, 2, false>(s, kp);
-	if (s->model == 0) return s->share ? launch_tma_t<STAGE, 0, true>(s, kp) : launch_tma_t<STAGE, 0, false>(s, kp);
-	return s->share ? launch_tma_t<STAGE, 1, true>(s, kp) : launch_tma_t<STAGE, 1, false>(s, kp);
+	if (s->share) {      // A/B variant, CTA barriers only
+		if (s->model == 2) return launch_tma_t<STAGE, 2, true, false>(s, kp);
+		if (s->model == 0) return launch_tma_t<STAGE, 0, true, false>(s, kp);
+		return launch_tma_t<STAGE, 1, true, false>(s, kp);
+	}
+	if (s->model == 2) return s->split ? launch_tma_t<STAGE, 2, false, true>(s, kp) : launch_tma_t<STAGE, 2, false, false>(s, kp);
+	if (s->model == 0) return s->split ? launch_tma_t<STAGE, 0, false, true>(s, kp) : launch_tma_t<STAGE, 0, false, false>(s, kp);
+	return s->split ? launch_tma_t<STAGE, 1, false, true>(s, kp) : launch_tma_t<STAGE, 1, false, false>(s, kp);
 }
 
 // stage launcher: fills the argument block for one Merson stage and (multi-GPU) exchanges the
@@ -573,6 +579,7 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	if (!s->heat) s->arr[A_XN][0] = s->arr[A_X][0];
 
 	s->use_tma = s->heat && !(flags & PFT_FLAG_LEGACY_LOADS) && !env_int("PFT_LEGACY", 0);
+	s->split = s->use_tma && !s->share && env_int("PFT_SPLIT", 0) != 0;
 	if (s->use_tma) {
 		s->bx = s->TX + 4;                   // box starts at x = i0-2 (16-byte aligned inner offset), TX is even
 		s->by = s->TY + 2;
@@ -582,7 +589,7 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 		for (int st = 1; st <= 5; st++) {
 			int na = 2 * stage_np(st) + 1;
 			bool form = !(st == 1 || st == 3);
-			s->smem_tma[st - 1] = ((size_t)TMA_STAGES * na * s->as + (form ? 4 * (size_t)s->as : 0) + fl) * sizeof(double);
+			s->smem_tma[st - 1] = ((size_t)TMA_STAGES * na * s->as + (form ? (s->split ? 6 : 4) * (size_t)s->as : 0) + fl) * sizeof(double);
 			worst = std::max(worst, s->smem_tma[st - 1]);
 		}
 		if (worst > 225 * 1024) { pft_destroy(s); return fail(PFT_EINVAL, "tile %dx%d needs %zu bytes of shared memory", s->TX, s->TY, worst); }

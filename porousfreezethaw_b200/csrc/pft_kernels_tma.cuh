@@ -58,6 +58,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	asm volatile(
@@ -79,10 +83,17 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
 }
 #else
 // CPU emulation (tests/cuda_emu): a tensor load is a synchronous box copy with zero fill; an
-// mbarrier is a completed-phase counter
-inline void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
+// mbarrier is {tx bytes pending [63:44], expected arrivals [43:32], pending arrivals [31:20], phase [19:0]}
+inline void emu_mbar_settle(uint64_t *bar)
+{
+	uint64_t tx = *bar >> 44, cnt = (*bar >> 32) & 0xfff, pend = (*bar >> 20) & 0xfff, ph = *bar & 0xfffff;
+	if (pend == 0 && tx == 0) { ph = (ph + 1) & 0xfffff; pend = cnt; }
+	*bar = (tx << 44) | (cnt << 32) | (pend << 20) | ph;
+}
+inline void mbar_init(uint64_t *bar, uint32_t count) { *bar = ((uint64_t)count << 32) | ((uint64_t)count << 20); }
 inline void fence_mbar_init() {}
-inline void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) { *bar += ((uint64_t)bytes << 32); }
+inline void mbar_arrive(uint64_t *bar) { *bar -= (1ull << 20); emu_mbar_settle(bar); }
+inline void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) { *bar += ((uint64_t)bytes << 44); *bar -= (1ull << 20); emu_mbar_settle(bar); }
 inline void mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	while ((uint32_t)(*bar & 1u) == parity) pft_emu::yield();
@@ -90,10 +101,8 @@ inline void mbar_wait(uint64_t *bar, uint32_t parity)
 inline void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
 {
 	uint32_t n = pft_emu::tensor_load_3d(dst, map, x, y, z);
-	uint64_t pending = (*bar >> 32) - n;
-	uint64_t phase = *bar & 0xffffffffull;
-	if (pending == 0) phase += 1;
-	*bar = (pending << 32) | phase;
+	*bar -= ((uint64_t)n << 44);
+	emu_mbar_settle(bar);
 }
 #endif
 
@@ -108,7 +117,16 @@ __device__ __forceinline__ double form_state(const double *buf, int as, int slot
 	return (0.5 * r[as] - 1.5 * r[2 * as] + 2.0 * r[3 * as]) * ha + r[0];                   // :449
 }
 
-template <int STAGE, int MODEL, bool SHARE>
+// one lane per warp arrives for the whole warp (the mbarrier is initialised with the warp count)
+__device__ __forceinline__ void warp_arrive(uint64_t *bar, int lane)
+{
+	__syncwarp();
+	if (lane == 0) mbar_arrive(bar);
+}
+
+// SPLIT: replace the CTA barrier that ends a plane by split-phase mbarriers (arrive now, wait one or
+// two planes later), so that warps may drift up to a plane apart instead of idling at a barrier
+template <int STAGE, int MODEL, bool SHARE, bool SPLIT>
 __global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant__ TmaParams P)
 {
 	const Consts &c = P.c;
@@ -121,18 +139,22 @@ __global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant
 	constexpr int NA = 2 * NP + 1;
 	constexpr bool FORM = !(STAGE == 1 || STAGE == 3);
 	constexpr int IU = NP, IG = 2 * NP;          // first u-type array, the gl array
+	constexpr int NT = FORM ? (SPLIT ? 3 : 2) : 0;   // state tile buffers
 
 	const int TX = blockDim.x, TY = blockDim.y;
 	const int tx = threadIdx.x, ty = threadIdx.y;
 	const int tid = ty * TX + tx;
+	const int lane = tid & 31;
 	const int BX = P.bx, AS = P.as;
 
 	PFT_DYN_SMEM_ALIGNED(double, smem_t);
 	double *raw = smem_t;                                            // [3][NA][AS]
-	double *tile = raw + TMA_STAGES * NA * AS;                       // [2][2][AS]   (FORM)
-	double *fxs = tile + (FORM ? 4 * AS : 0);                        // [TY][TX+1]   (SHARE)
+	double *tile = raw + TMA_STAGES * NA * AS;                       // [NT][2][AS]  (FORM)
+	double *fxs = tile + NT * 2 * AS;                                // [TY][TX+1]   (SHARE)
 	double *fys = fxs + (SHARE ? TY * (TX + 1) : 0);                 // [TY+1][TX]   (SHARE)
-	__shared__ uint64_t full[TMA_STAGES];
+	__shared__ uint64_t full[TMA_STAGES];    // raw plane landed (TMA complete_tx)
+	__shared__ uint64_t tready[3];           // SPLIT: state tile formed by every warp
+	__shared__ uint64_t done[2];             // SPLIT: every warp finished a plane (even / odd planes)
 
 	const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
 	const int i = i0 + tx, j = j0 + ty;
@@ -164,46 +186,42 @@ __global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant
 	const bool fduty = SHARE && tid < TX + TY;
 
 	if (tid == 0) {
-		for (int b = 0; b < TMA_STAGES; b++) mbar_init(&full[b], 1);
+		const int nwarps = (TX * TY + 31) >> 5;
+		for (int b = 0; b < TMA_STAGES; b++) { mbar_init(&full[b], 1); mbar_init(&tready[b], nwarps); }
+		mbar_init(&done[0], nwarps); mbar_init(&done[1], nwarps);
 		fence_mbar_init();
 	}
 	__syncthreads();
 
-	int next_q = qlo;            // thread 0: next plane to request
-	auto issue_upto = [&](int qmax) {
-		while (next_q <= qhi && next_q <= qmax) {
-			const int b = next_q % TMA_STAGES;
-			mbar_arrive_expect_tx(&full[b], (uint32_t)(NA * BX * P.by * sizeof(double)));
-			#pragma unroll
-			for (int m = 0; m < NA; m++)
-				tma_load_3d(raw + (b * NA + m) * AS, &P.maps[m], i0 - 2, j0 - 1, k0 + next_q, &full[b]);
-			next_q++;
-		}
+	// thread 0 requests plane q into raw buffer b: one tensor copy per array
+	const uint32_t plane_bytes = (uint32_t)(NA * BX * P.by * sizeof(double));
+	auto issue = [&](int q, int b) {
+		mbar_arrive_expect_tx(&full[b], plane_bytes);
+		#pragma unroll
+		for (int m = 0; m < NA; m++)
+			tma_load_3d(raw + (b * NA + m) * AS, &P.maps[m], i0 - 2, j0 - 1, k0 + q, &full[b]);
 	};
-	if (tid == 0) issue_upto(qlo + TMA_STAGES - 1);
+	int next_q = qlo;
+	if (tid == 0) {
+		#pragma unroll 1
+		for (int n = 0; n < TMA_STAGES && next_q <= qhi; n++, next_q++) issue(next_q, next_q % TMA_STAGES);
+	}
 
-	uint32_t phase_bits = 0;     // per-buffer parity of the next completion to wait for
-	auto wait_plane = [&](int q) {
-		const int b = q % TMA_STAGES;
-		mbar_wait(&full[b], (phase_bits >> b) & 1u);
-		phase_bits ^= (1u << b);
-	};
-
+	uint32_t full_bits = 0, tile_bits = 0;       // parity of the next completion to wait for, per buffer
 	double um, pm, gm, uc, pc, gc, un, pn, gn;
 	double fzm = 0.0, emax = 0.0;
 	int nonfinite = 0;
 
-	// ---- prologue
+	// ---- prologue: planes k0-1 (registers only) and k0 (registers + tile 0)
 	if (qlo == 0) {
-		wait_plane(0);
-		const double *rb = raw;
-		pm = form_state<STAGE>(rb, AS, cs, 0, a.ha);
-		um = form_state<STAGE>(rb, AS, cs, IU, a.ha);
-		gm = rb[IG * AS + cs];
+		mbar_wait(&full[0], 0); full_bits ^= 1u;
+		pm = form_state<STAGE>(raw, AS, cs, 0, a.ha);
+		um = form_state<STAGE>(raw, AS, cs, IU, a.ha);
+		gm = raw[IG * AS + cs];
 	}
 	{
-		wait_plane(1);
-		const double *rb = raw + (1 % TMA_STAGES) * NA * AS;
+		mbar_wait(&full[1], 0); full_bits ^= 2u;
+		const double *rb = raw + NA * AS;
 		pc = form_state<STAGE>(rb, AS, cs, 0, a.ha);
 		uc = form_state<STAGE>(rb, AS, cs, IU, a.ha);
 		gc = rb[IG * AS + cs];
@@ -216,35 +234,47 @@ __global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant
 	}
 	__syncthreads();
 
-	int cur = 0;
-	int bq = 1, bn = 2;          // raw buffers of plane q (centre) and q+1; (q+2) % 3 == the third one
-	for (int k = k0; k < k1; ++k) {
-		const int q = k - k0 + 1;
+	int bq = 1, bn = 2, bf = 0;  // raw buffers of plane q (centre), q+1 (next), q+2 (to be requested)
+	int tc = 0, tn = 1;          // state tiles of plane k and k+1
+	for (int it = 0, k = k0; k < k1; ++k, ++it) {
+		const int q = it + 1;
 		const bool more = (k + 1 < k1);
 		const double *rb = raw + bq * NA * AS;                        // raw planes of the centre plane k
 		const double *rg = rb + IG * AS;
 
-		if (tid == 0) issue_upto(q + 2);      // its buffer held plane q-1, released by the barrier below
+		// ---- thread 0: request plane q+2 into the buffer plane q-1 just vacated
+		if (tid == 0 && next_q <= qhi && next_q <= q + 2) {
+			if (SPLIT && it >= 1) mbar_wait(&done[(it - 1) & 1], ((it - 1) >> 1) & 1);
+			issue(next_q, bf);
+			next_q++;
+		}
 
-		// ---- plane k+1: form the stage input (centre -> registers, centre + ring -> the other tile)
+		// ---- plane k+1: form the stage input (centre -> registers, centre + ring -> its state tile)
 		if (q + 1 <= qhi) {
-			mbar_wait(&full[bn], (phase_bits >> bn) & 1u);
-			phase_bits ^= (1u << bn);
+			// SPLIT: tile[tn] was last read while plane k-2 was computed
+			if (SPLIT && FORM && more && it >= 2) mbar_wait(&done[it & 1], ((it - 2) >> 1) & 1);
+			mbar_wait(&full[bn], (full_bits >> bn) & 1u);
+			full_bits ^= (1u << bn);
 			const double *rn = raw + bn * NA * AS;
 			pn = form_state<STAGE>(rn, AS, cs, 0, a.ha);
 			un = form_state<STAGE>(rn, AS, cs, IU, a.ha);
 			gn = rn[IG * AS + cs];
 			if (FORM && more) {
-				double *tn = tile + (cur ^ 1) * 2 * AS;
-				tn[cs] = pn; tn[AS + cs] = un;
-				if (hduty) { tn[hs] = form_state<STAGE>(rn, AS, hs, 0, a.ha); tn[AS + hs] = form_state<STAGE>(rn, AS, hs, IU, a.ha); }
+				double *tw = tile + tn * 2 * AS;
+				tw[cs] = pn; tw[AS + cs] = un;
+				if (hduty) { tw[hs] = form_state<STAGE>(rn, AS, hs, 0, a.ha); tw[AS + hs] = form_state<STAGE>(rn, AS, hs, IU, a.ha); }
+				if (SPLIT) warp_arrive(&tready[tn], lane);
 			}
 		} else {
 			un = a.dir_u; pn = pc; gn = gc;                             // equation.c:175-183 / :251-261
 		}
 
 		// ---- plane k
-		const double *tp = FORM ? tile + cur * 2 * AS : rb;
+		if (SPLIT && FORM && it >= 1) {                                 // its tile was formed while plane k-1 was computed
+			mbar_wait(&tready[tc], (tile_bits >> tc) & 1u);
+			tile_bits ^= (1u << tc);
+		}
+		const double *tp = FORM ? tile + tc * 2 * AS : rb;
 		const double *tu = FORM ? tp + AS : rb + IU * AS;
 		const double pw = tp[sW], pe = tp[sE], ps = tp[sS], pnn = tp[sN];
 
@@ -272,6 +302,7 @@ __global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant
 				__syncthreads();
 				fw = fxs[ty * (TX + 1) + tx];
 				fs = fys[ty * TX + tx];
+				__syncthreads();      // (SHARE is the A/B variant: keep it simple and safe)
 			} else {
 				fw = face_flux(c, pw, pc, rg[sW], gc, tu[sW], uc);
 				fs = face_flux(c, ps, pc, rg[sS], gc, tu[sS], uc);
@@ -330,11 +361,13 @@ __global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant
 			}
 		}
 
-		__syncthreads();        // tile[cur^1] complete; raw buffer of plane k-1.. free for thread 0
+		// ---- this plane is done: raw[bq] may be refilled, tile[tc] overwritten (two planes later)
+		if (SPLIT) warp_arrive(&done[it & 1], lane);
+		else __syncthreads();
 		um = uc; pm = pc; gm = gc;
 		uc = un; pc = pn; gc = gn;
-		cur ^= 1;
-		{ const int b3 = 3 - bq - bn; bq = bn; bn = b3; }
+		{ const int t = bq; bq = bn; bn = bf; bf = t; }
+		if (FORM) { tc = tn; tn = (tn + 1 == NT) ? 0 : tn + 1; }
 	}
 
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);

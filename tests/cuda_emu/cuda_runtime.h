@@ -36,6 +36,7 @@ extern unsigned char *g_dyn_smem;
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body);
 void syncthreads();
 void yield();                        // let the other fibers of the CTA run (spin-wait loops)
+void syncwarp();                     // barrier among the fibers of one warp (32 consecutive linear thread ids)
 struct CUtensorMap_fwd;
 uint32_t tensor_load_3d(void *dst, const void *map, int x, int y, int z);   // returns the bytes written
 }
@@ -56,6 +57,7 @@ uint32_t tensor_load_3d(void *dst, const void *map, int x, int y, int z);   // r
 #define PFT_DYN_SMEM_ALIGNED(type, name) type *name = reinterpret_cast<type *>(pft_emu::g_dyn_smem)
 
 static inline void __syncthreads() { pft_emu::syncthreads(); }
+static inline void __syncwarp() { pft_emu::syncwarp(); }
 static inline void __threadfence() {}
 static inline void __threadfence_system() {}
 

@@ -5,6 +5,7 @@
 #include "cuda.h"
 #include <ucontext.h>
 #include <stdio.h>
+#include <algorithm>
 #include <vector>
 
 namespace pft_emu {
@@ -35,6 +36,16 @@ void syncthreads()
 {
 	fibers[cur].state = WAITING;
 	swapcontext(&fibers[cur].ctx, &sched_ctx);
+}
+
+static int w_count[64], w_gen[64], w_size[64];
+
+void syncwarp()
+{
+	const int w = cur >> 5;
+	const int gen = w_gen[w];
+	if (++w_count[w] == w_size[w]) { w_count[w] = 0; w_gen[w]++; }
+	else while (w_gen[w] == gen) yield();
 }
 
 void yield()
@@ -85,6 +96,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 			makecontext(&f.ctx, trampoline, 0);
 			f.state = READY; f.tid = uint3{x, y, z};
 		}
+		for (int w = 0; w < 64; w++) { w_count[w] = 0; w_gen[w] = 0; w_size[w] = std::max(0, std::min(32, nt - 32 * w)); }
 		int alive = nt;
 		while (alive > 0) {
 			int waiting = 0;
