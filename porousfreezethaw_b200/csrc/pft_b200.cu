@@ -169,6 +169,7 @@ struct pft_solver {
 	// TMA path (heat modes): one tensor map per array, box = tile + halo ring
 	bool use_tma;
 	bool split;           // split-phase mbarriers instead of a CTA barrier per plane
+	bool rows2;           // two vertically adjacent cells per thread (merson_stage_tma2)
 	CUtensorMap tmap[A_COUNT][2];
 	CUtensorMap tmap_gl;
 	int bx, by, as;
@@ -336,9 +337,28 @@ static cudaError_t launch_tma_t(pft_solver *s, const TmaParams &kp)
 	return cudaGetLastError();
 }
 
+template <int STAGE, int MODEL>
+static cudaError_t launch_tma2_t(pft_solver *s, const TmaParams &kp)
+{
+	auto fn = merson_stage_tma2<STAGE, MODEL>;
+	static bool attr_set = false;
+	if (!attr_set) {
+		cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+		if (e != cudaSuccess) return e;
+		attr_set = true;
+	}
+	PFT_LAUNCH(fn, s->grid, s->block, s->smem_tma[STAGE - 1], s->stream, kp);
+	return cudaGetLastError();
+}
+
 template <int STAGE>
 static cudaError_t launch_stage_tma_t(pft_solver *s, const TmaParams &kp)
 {
+	if (s->rows2) {
+		if (s->model == 2) return launch_tma2_t<STAGE, 2>(s, kp);
+		if (s->model == 0) return launch_tma2_t<STAGE, 0>(s, kp);
+		return launch_tma2_t<STAGE, 1>(s, kp);
+	}
 	if (s->share) {      // A/B variant, CTA barriers only
 		if (s->model == 2) return launch_tma_t<STAGE, 2, true, false>(s, kp);
 		if (s->model == 0) return launch_tma_t<STAGE, 0, true, false>(s, kp);
@@ -533,25 +553,30 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	s->N1 = cs->n1 + 2 * PFT_BT; s->N2 = cs->n2 + 2 * PFT_BT; s->N3 = cs->n3 + 2 * PFT_BT;
 	s->padded = (long long)PFT_NVAR * s->N1 * s->N2 * s->N3;
 
-	int max_threads = env_int("PFT_THREADS", 256);     // two or three CTAs per SM overlap each other's barrier waits
-	if (max_threads < 64) max_threads = 64;
+	s->use_tma = s->heat && !(flags & PFT_FLAG_LEGACY_LOADS) && !env_int("PFT_LEGACY", 0);
+	s->rows2 = s->use_tma && !s->share && env_int("PFT_ROWS2", 0) != 0;    // measured slower than one cell per thread (profiles/round1_tuning.md)
+	const int rpt = s->rows2 ? 2 : 1;        // cell rows per thread
+	int max_threads = env_int("PFT_THREADS", s->rows2 ? 160 : 256);     // two or three CTAs per SM overlap each other's barrier waits
+	if (max_threads < 32) max_threads = 32;
 	if (max_threads > 512) max_threads = 512;
-	choose_tile(cs->n1, cs->n2, max_threads, &s->TX, &s->TY);
+	if (s->use_tma && max_threads > 256) max_threads = 256;      // __launch_bounds__ of the TMA kernels
+	choose_tile(cs->n1, (cs->n2 + rpt - 1) / rpt, max_threads, &s->TX, &s->TY);
 	if (env_int("PFT_TX", 0) > 0) s->TX = env_int("PFT_TX", 0);
 	if (env_int("PFT_TY", 0) > 0) s->TY = env_int("PFT_TY", 0);
 	if (s->TX & 1) s->TX++;                  // tile origins must be even (TMA inner-offset alignment)
-	if (s->TX * s->TY > 512 || s->TX * s->TY < 2 * s->TX + 2 * s->TY) {
+	if (s->TX * s->TY > (s->use_tma ? 256 : 512) || rpt * s->TX * s->TY < 2 * s->TX + 2 * rpt * s->TY) {
 		int tx_ = s->TX, ty_ = s->TY;
 		delete s;
-		return fail(PFT_EINVAL, "tile %dx%d unusable (needs TX*TY <= 512 and >= 2*TX+2*TY)", tx_, ty_);
+		return fail(PFT_EINVAL, "tile %dx%d unusable (needs TX*TY <= 512 and enough threads for the halo ring)", tx_, ty_);
 	}
-	int tiles_xy = ((cs->n1 + s->TX - 1) / s->TX) * ((cs->n2 + s->TY - 1) / s->TY);
-	int ctas_per_sm = std::max(1, 512 / (s->TX * s->TY));
+	const int tile_rows = rpt * s->TY;
+	int tiles_xy = ((cs->n1 + s->TX - 1) / s->TX) * ((cs->n2 + tile_rows - 1) / tile_rows);
+	int ctas_per_sm = std::max(1, 512 / (rpt * s->TX * s->TY));
 	s->nzc = choose_chunks(tiles_xy, cs->n3, prop.multiProcessorCount * ctas_per_sm);
 	if (env_int("PFT_ZCHUNKS", 0) > 0) s->nzc = std::min(cs->n3, env_int("PFT_ZCHUNKS", 0));
 	g.zc = (cs->n3 + s->nzc - 1) / s->nzc;
 	s->nzc = (cs->n3 + g.zc - 1) / g.zc;
-	s->grid = dim3((cs->n1 + s->TX - 1) / s->TX, (cs->n2 + s->TY - 1) / s->TY, s->nzc);
+	s->grid = dim3((cs->n1 + s->TX - 1) / s->TX, (cs->n2 + tile_rows - 1) / tile_rows, s->nzc);
 	s->block = dim3(s->TX, s->TY, 1);
 	{
 		int NF = s->heat ? 3 : 1;
@@ -578,18 +603,17 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	CU(cudaMemsetAsync(s->gl, 0, fb, s->stream));
 	if (!s->heat) s->arr[A_XN][0] = s->arr[A_X][0];
 
-	s->use_tma = s->heat && !(flags & PFT_FLAG_LEGACY_LOADS) && !env_int("PFT_LEGACY", 0);
 	s->split = s->use_tma && !s->share && env_int("PFT_SPLIT", 0) != 0;
 	if (s->use_tma) {
 		s->bx = s->TX + 4;                   // box starts at x = i0-2 (16-byte aligned inner offset), TX is even
-		s->by = s->TY + 2;
+		s->by = (s->rows2 ? 2 : 1) * s->TY + 2;
 		s->as = (s->bx * s->by + 15) & ~15;  // each array buffer starts 128-byte aligned
 		size_t fl = s->share ? (size_t)s->TY * (s->TX + 1) + (size_t)(s->TY + 1) * s->TX : 0;
 		size_t worst = 0;
 		for (int st = 1; st <= 5; st++) {
 			int na = 2 * stage_np(st) + 1;
 			bool form = !(st == 1 || st == 3);
-			s->smem_tma[st - 1] = ((size_t)TMA_STAGES * na * s->as + (form ? (s->split ? 6 : 4) * (size_t)s->as : 0) + fl) * sizeof(double);
+			s->smem_tma[st - 1] = ((size_t)TMA_STAGES * na * s->as + (form ? (s->split && !s->rows2 ? 6 : 4) * (size_t)s->as : 0) + fl) * sizeof(double);
 			worst = std::max(worst, s->smem_tma[st - 1]);
 		}
 		if (worst > 225 * 1024) { pft_destroy(s); return fail(PFT_EINVAL, "tile %dx%d needs %zu bytes of shared memory", s->TX, s->TY, worst); }

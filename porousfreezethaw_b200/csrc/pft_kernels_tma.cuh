@@ -117,6 +117,67 @@ __device__ __forceinline__ double form_state(const double *buf, int as, int slot
 	return (0.5 * r[as] - 1.5 * r[2 * as] + 2.0 * r[3 * as]) * ha + r[0];                   // :449
 }
 
+// everything of the right-hand side of one cell that comes after the face fluxes
+template <int MODEL>
+__device__ __forceinline__ void cell_rhs(const Consts &c, double uc, double pc, double gc,
+                                         double pw, double pe, double ps, double pnn, double pm, double pn,
+                                         double sum, double &du, double &dp)
+{
+	const double rho = mix3(pc, gc, c.g_rho, c.i_rho, c.w_rho);
+	const double cp = mix3(pc, gc, c.g_cp, c.i_cp, c.w_cp);
+	const double wi = 1.0 - c.zeta * gc;
+	const double ind = (wi > 0.0) ? wi : 0.0;                                                // fmax(0, .), equation.c:362
+	if (MODEL == 2) {
+		double ch = cosh(c.gamma * (uc - c.u_star));                                           // equation.c:835-867
+		double dp_du = (-0.5 * c.gamma / (ch * ch)) * ind;
+		du = div_pos(sum, rho * (cp - c.L * dp_du));
+		dp = dp_du * du;
+	} else {
+		dp = c.h1_2 * (-(-pw + pc) + (-pc + pe))                                               // equation.c:659-669
+		   + c.h2_2 * (-(-ps + pc) + (-pc + pnn))
+		   + c.h3_2 * (-(-pm + pc) + (-pc + pn));
+		double one_m_p = 1.0 - pc;
+		double well = c.xi_2_inv_a * pc * one_m_p * (pc - 0.5);
+		double du_star = uc - c.u_star;
+		if (MODEL == 0) {
+			double gx = c.h1_d2 * (-pw + pe), gy = c.h2_d2 * (-ps + pnn), gz = c.h3_d2 * (-pm + pn);
+			double nrm = sqrt(gx * gx + gy * gy + gz * gz) + 1E-10;                           // :332-336
+			dp += well - c.bam * nrm * du_star;                                                   // :370
+		} else {
+			double pq = pc * one_m_p;
+			double pqm = (pq >= 0.0) ? pq : 0.0;                                                  // fmax(., 0), :387
+			dp += well - c.sam * sshape(c, pc) * sshape(c, one_m_p) * pqm * du_star;
+		}
+		dp = div_pos(dp, c.alpha);
+		dp *= ind;
+		du = div_pos(div_pos(sum, rho) + c.L * dp, cp);                                           // :711-723
+	}
+}
+
+// the fused combination that follows stage STAGE, for one cell (operands from the raw buffer)
+template <int STAGE>
+__device__ __forceinline__ void stage_output(const StageArgs &a, const double *rb, int AS, int IU, int cs, long long o,
+                                             double du, double dp, double &emax, int &nonfinite)
+{
+	if (STAGE == 1 || STAGE == 3 || STAGE == 4) {
+		a.op[o] = dp;
+		a.ou[o] = du;
+	} else if (STAGE == 2) {
+		a.op[o] = (rb[AS + cs] + dp) * a.hb + rb[cs];                                           // hybrid2.c:408
+		a.ou[o] = (rb[(IU + 1) * AS + cs] + du) * a.hb + rb[IU * AS + cs];
+	} else {
+		const double xp = rb[cs], k1p = rb[AS + cs], k3p = rb[2 * AS + cs], k4p = rb[3 * AS + cs];
+		const double xu = rb[IU * AS + cs], k1u = rb[(IU + 1) * AS + cs], k3u = rb[(IU + 2) * AS + cs], k4u = rb[(IU + 3) * AS + cs];
+		double e = fabs(0.2 * k1p - 0.9 * k3p + 0.8 * k4p - 0.1 * dp);                          // :521
+		double eu = fabs(0.2 * k1u - 0.9 * k3u + 0.8 * k4u - 0.1 * du);
+		if (!(e <= 1.7976931348623157e308) || !(eu <= 1.7976931348623157e308)) nonfinite = 1;
+		emax = (e > emax) ? e : emax;
+		emax = (eu > emax) ? eu : emax;
+		a.op[o] = xp + a.hb * (0.5 * (k1p + dp) + 2.0 * k4p);                                   // :667
+		a.ou[o] = xu + a.hb * (0.5 * (k1u + du) + 2.0 * k4u);
+	}
+}
+
 // one lane per warp arrives for the whole warp (the mbarrier is initialised with the warp count)
 __device__ __forceinline__ void warp_arrive(uint64_t *bar, int lane)
 {
@@ -127,7 +188,7 @@ __device__ __forceinline__ void warp_arrive(uint64_t *bar, int lane)
 // SPLIT: replace the CTA barrier that ends a plane by split-phase mbarriers (arrive now, wait one or
 // two planes later), so that warps may drift up to a plane apart instead of idling at a barrier
 template <int STAGE, int MODEL, bool SHARE, bool SPLIT>
-__global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant__ TmaParams P)
+__global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_stage_tma(const __grid_constant__ TmaParams P)
 {
 	const Consts &c = P.c;
 	const Geom &g = P.g;
@@ -313,52 +374,12 @@ __global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant
 		}
 
 		double du, dp;
-		const double rho = mix3(pc, gc, c.g_rho, c.i_rho, c.w_rho);
-		const double cp = mix3(pc, gc, c.g_cp, c.i_cp, c.w_cp);
-		if (MODEL == 2) {
-			double ch = cosh(c.gamma * (uc - c.u_star));                                   // equation.c:835-867
-			double dp_du = (-0.5 * c.gamma / (ch * ch)) * fmax(0.0, 1.0 - c.zeta * gc);
-			du = div_pos(sum, rho * (cp - c.L * dp_du));
-			dp = dp_du * du;
-		} else {
-			dp = c.h1_2 * (-(-pw + pc) + (-pc + pe))                                       // equation.c:659-669
-			   + c.h2_2 * (-(-ps + pc) + (-pc + pnn))
-			   + c.h3_2 * (-(-pm + pc) + (-pc + pn));
-			double one_m_p = 1.0 - pc;
-			double well = c.xi_2_inv_a * pc * one_m_p * (pc - 0.5);
-			double du_star = uc - c.u_star;
-			if (MODEL == 0) {
-				double gx = c.h1_d2 * (-pw + pe), gy = c.h2_d2 * (-ps + pnn), gz = c.h3_d2 * (-pm + pn);
-				double nrm = sqrt(gx * gx + gy * gy + gz * gz) + 1E-10;                   // :332-336
-				dp += well - c.bam * nrm * du_star;                                           // :370
-			} else {
-				dp += well - c.sam * sshape(c, pc) * sshape(c, one_m_p) * fmax(pc * one_m_p, 0.0) * du_star;   // :387
-			}
-			dp = div_pos(dp, c.alpha);
-			dp *= fmax(0.0, 1.0 - c.zeta * gc);
-			du = div_pos(div_pos(sum, rho) + c.L * dp, cp);                                   // :711-723
-		}
+		cell_rhs<MODEL>(c, uc, pc, gc, pw, pe, ps, pnn, pm, pn, sum, du, dp);
 
 		// ---- fused combination that follows this stage (operands re-read from the raw buffer)
 		if (active) {
 			const long long o = (long long)(k + 1) * g.plane + (long long)j * g.px + i;
-			if (STAGE == 1 || STAGE == 3 || STAGE == 4) {
-				a.op[o] = dp;
-				a.ou[o] = du;
-			} else if (STAGE == 2) {
-				a.op[o] = (rb[AS + cs] + dp) * a.hb + rb[cs];                               // hybrid2.c:408
-				a.ou[o] = (rb[(IU + 1) * AS + cs] + du) * a.hb + rb[IU * AS + cs];
-			} else {
-				const double xp = rb[cs], k1p = rb[AS + cs], k3p = rb[2 * AS + cs], k4p = rb[3 * AS + cs];
-				const double xu = rb[IU * AS + cs], k1u = rb[(IU + 1) * AS + cs], k3u = rb[(IU + 2) * AS + cs], k4u = rb[(IU + 3) * AS + cs];
-				double e = fabs(0.2 * k1p - 0.9 * k3p + 0.8 * k4p - 0.1 * dp);              // :521
-				double eu = fabs(0.2 * k1u - 0.9 * k3u + 0.8 * k4u - 0.1 * du);
-				if (!(e <= 1.7976931348623157e308) || !(eu <= 1.7976931348623157e308)) nonfinite = 1;
-				emax = (e > emax) ? e : emax;
-				emax = (eu > emax) ? eu : emax;
-				a.op[o] = xp + a.hb * (0.5 * (k1p + dp) + 2.0 * k4p);                       // :667
-				a.ou[o] = xu + a.hb * (0.5 * (k1u + du) + 2.0 * k4u);
-			}
+			stage_output<STAGE>(a, rb, AS, IU, cs, o, du, dp, emax, nonfinite);
 		}
 
 		// ---- this plane is done: raw[bq] may be refilled, tile[tc] overwritten (two planes later)
@@ -368,6 +389,193 @@ __global__ void __launch_bounds__(512, 1) merson_stage_tma(const __grid_constant
 		uc = un; pc = pn; gc = gn;
 		{ const int t = bq; bq = bn; bn = bf; bf = t; }
 		if (FORM) { tc = tn; tn = (tn + 1 == NT) ? 0 : tn + 1; }
+	}
+
+	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
+}
+
+// ----------------------------------------------------------------------------------------
+// merson_stage_tma2: as merson_stage_tma, but every thread owns TWO vertically adjacent cells
+// (rows 2*ty and 2*ty+1 of a TX x 2*TY tile).  The face between them is computed once, the
+// address arithmetic, constant fetches and loop control are paid once per two cells, and the two
+// independent dependency chains double the instruction-level parallelism the fp64 pipe sees.
+
+template <int STAGE, int MODEL>
+__global__ void __launch_bounds__(256, 2) merson_stage_tma2(const __grid_constant__ TmaParams P)
+{
+	const Consts &c = P.c;
+	const Geom &g = P.g;
+	const StageArgs &a = P.a;
+
+	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) return; }
+
+	constexpr int NP = stage_np(STAGE);
+	constexpr int NA = 2 * NP + 1;
+	constexpr bool FORM = !(STAGE == 1 || STAGE == 3);
+	constexpr int IU = NP, IG = 2 * NP;
+
+	const int TX = blockDim.x, TY = blockDim.y, RY = 2 * TY;       // tile = TX x RY cells
+	const int tx = threadIdx.x, ty = threadIdx.y;
+	const int tid = ty * TX + tx, nthr = TX * TY;
+	const int BX = P.bx, AS = P.as;
+
+	PFT_DYN_SMEM_ALIGNED(double, smem_t);
+	double *raw = smem_t;                                            // [3][NA][AS]
+	double *tile = raw + TMA_STAGES * NA * AS;                       // [2][2][AS]  (FORM)
+	__shared__ uint64_t full[TMA_STAGES];
+
+	const int i0 = blockIdx.x * TX, j0 = blockIdx.y * RY;
+	const int i = i0 + tx, jA = j0 + 2 * ty, jB = jA + 1;
+	const bool actA = (i < g.n1) && (jA < g.n2), actB = (i < g.n1) && (jB < g.n2);
+	const bool hasB = jB < g.n2;                                     // else A's upper neighbour is its own mirror
+	const int csA = (2 * ty + 1) * BX + (tx + 2), csB = csA + BX;
+	// in-plane neighbour slots, clamped to the DOMAIN (zero-Neumann mirror, equation.c:142-160)
+	const int dW = (i > 0) ? -1 : 0, dE = (i < g.n1 - 1) ? 1 : 0;
+	const int sS = (jA > 0) ? csA - BX : csA;                        // below A
+	const int sN = (jB < g.n2 - 1) ? csB + BX : csB;                 // above B
+
+	const int k0 = blockIdx.z * g.zc;
+	const int k1 = min(g.n3, k0 + g.zc);
+	const int qlo = (k0 == 0 && g.front) ? 1 : 0;
+	const int qhi = (k1 == g.n3 && g.rear) ? (k1 - k0) : (k1 - k0 + 1);
+
+	// ring duty (FORM): 2*TX + 2*RY ring cells, up to two per thread
+	int hs0 = -1, hs1 = -1;
+	if (FORM) {
+		const int nring = 2 * TX + 2 * RY;
+		#pragma unroll
+		for (int r = 0; r < 2; r++) {
+			const int h = tid + r * nthr;
+			int slot = -1;
+			if (h < nring) {
+				int hx, hy;
+				if (h < TX) { hx = h; hy = -1; }
+				else if (h < 2 * TX) { hx = h - TX; hy = RY; }
+				else if (h < 2 * TX + RY) { hx = -1; hy = h - 2 * TX; }
+				else { hx = TX; hy = h - 2 * TX - RY; }
+				slot = (hy + 1) * BX + (hx + 2);
+			}
+			if (r == 0) hs0 = slot; else hs1 = slot;
+		}
+	}
+
+	if (tid == 0) {
+		for (int b = 0; b < TMA_STAGES; b++) mbar_init(&full[b], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+
+	const uint32_t plane_bytes = (uint32_t)(NA * BX * P.by * sizeof(double));
+	auto issue = [&](int q, int b) {
+		mbar_arrive_expect_tx(&full[b], plane_bytes);
+		#pragma unroll
+		for (int m = 0; m < NA; m++)
+			tma_load_3d(raw + (b * NA + m) * AS, &P.maps[m], i0 - 2, j0 - 1, k0 + q, &full[b]);
+	};
+	int next_q = qlo;
+	if (tid == 0) {
+		#pragma unroll 1
+		for (int n = 0; n < TMA_STAGES && next_q <= qhi; n++, next_q++) issue(next_q, next_q % TMA_STAGES);
+	}
+
+	uint32_t full_bits = 0;
+	double umA, pmA, gmA, ucA, pcA, gcA, unA, pnA, gnA;
+	double umB, pmB, gmB, ucB, pcB, gcB, unB, pnB, gnB;
+	double fzA = 0.0, fzB = 0.0, emax = 0.0;
+	int nonfinite = 0;
+
+	// ---- prologue
+	if (qlo == 0) {
+		mbar_wait(&full[0], 0); full_bits ^= 1u;
+		pmA = form_state<STAGE>(raw, AS, csA, 0, a.ha); umA = form_state<STAGE>(raw, AS, csA, IU, a.ha); gmA = raw[IG * AS + csA];
+		pmB = form_state<STAGE>(raw, AS, csB, 0, a.ha); umB = form_state<STAGE>(raw, AS, csB, IU, a.ha); gmB = raw[IG * AS + csB];
+	}
+	{
+		mbar_wait(&full[1], 0); full_bits ^= 2u;
+		const double *rb = raw + NA * AS;
+		pcA = form_state<STAGE>(rb, AS, csA, 0, a.ha); ucA = form_state<STAGE>(rb, AS, csA, IU, a.ha); gcA = rb[IG * AS + csA];
+		pcB = form_state<STAGE>(rb, AS, csB, 0, a.ha); ucB = form_state<STAGE>(rb, AS, csB, IU, a.ha); gcB = rb[IG * AS + csB];
+		if (FORM) {
+			tile[csA] = pcA; tile[AS + csA] = ucA; tile[csB] = pcB; tile[AS + csB] = ucB;
+			if (hs0 >= 0) { tile[hs0] = form_state<STAGE>(rb, AS, hs0, 0, a.ha); tile[AS + hs0] = form_state<STAGE>(rb, AS, hs0, IU, a.ha); }
+			if (hs1 >= 0) { tile[hs1] = form_state<STAGE>(rb, AS, hs1, 0, a.ha); tile[AS + hs1] = form_state<STAGE>(rb, AS, hs1, IU, a.ha); }
+		}
+		if (qlo == 1) { umA = ucA; pmA = pcA; gmA = gcA; umB = ucB; pmB = pcB; gmB = gcB; }   // equation.c:164-174
+		fzA = face_flux(c, pmA, pcA, gmA, gcA, umA, ucA);
+		fzB = face_flux(c, pmB, pcB, gmB, gcB, umB, ucB);
+	}
+	__syncthreads();
+
+	int bq = 1, bn = 2, bf = 0, cur = 0;
+	for (int it = 0, k = k0; k < k1; ++k, ++it) {
+		const int q = it + 1;
+		const bool more = (k + 1 < k1);
+		const double *rb = raw + bq * NA * AS;
+		const double *rg = rb + IG * AS;
+
+		if (tid == 0 && next_q <= qhi && next_q <= q + 2) { issue(next_q, bf); next_q++; }
+
+		// ---- plane k+1: stage input (centres -> registers, centres + ring -> the other tile)
+		if (q + 1 <= qhi) {
+			mbar_wait(&full[bn], (full_bits >> bn) & 1u);
+			full_bits ^= (1u << bn);
+			const double *rn = raw + bn * NA * AS;
+			pnA = form_state<STAGE>(rn, AS, csA, 0, a.ha); unA = form_state<STAGE>(rn, AS, csA, IU, a.ha); gnA = rn[IG * AS + csA];
+			pnB = form_state<STAGE>(rn, AS, csB, 0, a.ha); unB = form_state<STAGE>(rn, AS, csB, IU, a.ha); gnB = rn[IG * AS + csB];
+			if (FORM && more) {
+				double *tw = tile + (cur ^ 1) * 2 * AS;
+				tw[csA] = pnA; tw[AS + csA] = unA; tw[csB] = pnB; tw[AS + csB] = unB;
+				if (hs0 >= 0) { tw[hs0] = form_state<STAGE>(rn, AS, hs0, 0, a.ha); tw[AS + hs0] = form_state<STAGE>(rn, AS, hs0, IU, a.ha); }
+				if (hs1 >= 0) { tw[hs1] = form_state<STAGE>(rn, AS, hs1, 0, a.ha); tw[AS + hs1] = form_state<STAGE>(rn, AS, hs1, IU, a.ha); }
+			}
+		} else {
+			unA = a.dir_u; pnA = pcA; gnA = gcA;                        // equation.c:175-183 / :251-261
+			unB = a.dir_u; pnB = pcB; gnB = gcB;
+		}
+
+		// ---- plane k, cells A (lower) and B (upper)
+		const double *tp = FORM ? tile + cur * 2 * AS : rb;
+		const double *tu = FORM ? tp + AS : rb + IU * AS;
+		const double pwA = tp[csA + dW], peA = tp[csA + dE], psA = tp[sS];
+		const double pwB = tp[csB + dW], peB = tp[csB + dE], pnB_ = tp[sN];
+		const double uwA = tu[csA + dW], ueA = tu[csA + dE], usA = tu[sS];
+		const double uwB = tu[csB + dW], ueB = tu[csB + dE], unB_ = tu[sN];
+		const double gwA = rg[csA + dW], geA = rg[csA + dE], gsA = rg[sS];
+		const double gwB = rg[csB + dW], geB = rg[csB + dE], gnB_ = rg[sN];
+		// A's upper neighbour: B, or A itself when B lies outside the domain (mirror)
+		const double pUp = hasB ? pcB : pcA, uUp = hasB ? ucB : ucA, gUp = hasB ? gcB : gcA;
+
+		const double fAB = face_flux(c, pcA, pUp, gcA, gUp, ucA, uUp);
+		double sumA, sumB;
+		{
+			double fw = face_flux(c, pwA, pcA, gwA, gcA, uwA, ucA);
+			double fe = face_flux(c, pcA, peA, gcA, geA, ucA, ueA);
+			double fs = face_flux(c, psA, pcA, gsA, gcA, usA, ucA);
+			double fz = face_flux(c, pcA, pnA, gcA, gnA, ucA, unA);
+			sumA = c.h1_2 * (-fw + fe) + c.h2_2 * (-fs + fAB) + c.h3_2 * (-fzA + fz);          // equation.c:711-720
+			fzA = fz;
+		}
+		{
+			double fw = face_flux(c, pwB, pcB, gwB, gcB, uwB, ucB);
+			double fe = face_flux(c, pcB, peB, gcB, geB, ucB, ueB);
+			double fn = face_flux(c, pcB, pnB_, gcB, gnB_, ucB, unB_);
+			double fz = face_flux(c, pcB, pnB, gcB, gnB, ucB, unB);
+			sumB = c.h1_2 * (-fw + fe) + c.h2_2 * (-fAB + fn) + c.h3_2 * (-fzB + fz);
+			fzB = fz;
+		}
+		double duA, dpA, duB, dpB;
+		cell_rhs<MODEL>(c, ucA, pcA, gcA, pwA, peA, psA, pUp, pmA, pnA, sumA, duA, dpA);
+		cell_rhs<MODEL>(c, ucB, pcB, gcB, pwB, peB, pcA, pnB_, pmB, pnB, sumB, duB, dpB);
+
+		const long long oA = (long long)(k + 1) * g.plane + (long long)jA * g.px + i;
+		if (actA) stage_output<STAGE>(a, rb, AS, IU, csA, oA, duA, dpA, emax, nonfinite);
+		if (actB) stage_output<STAGE>(a, rb, AS, IU, csB, oA + g.px, duB, dpB, emax, nonfinite);
+
+		__syncthreads();
+		umA = ucA; pmA = pcA; gmA = gcA; ucA = unA; pcA = pnA; gcA = gnA;
+		umB = ucB; pmB = pcB; gmB = gcB; ucB = unB; pcB = pnB; gcB = gnB;
+		cur ^= 1;
+		{ const int t = bq; bq = bn; bn = bf; bf = t; }
 	}
 
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);

@@ -50,6 +50,7 @@ uint32_t tensor_load_3d(void *dst, const void *map, int x, int y, int z);   // r
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __shared__ static

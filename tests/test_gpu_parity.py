@@ -47,7 +47,7 @@ def test_fused_stages_mode2(gpu_lib):
     parity.check_fused_stages(cases.small_case(24, 20, 32, calc_mode=2), gpu_lib, exact=False)
 
 
-@pytest.mark.parametrize("tx,ty,zc", [(5, 4, 3), (32, 8, 2), (7, 9, 5), (64, 8, 1)])
+@pytest.mark.parametrize("tx,ty,zc", [(5, 4, 3), (32, 8, 2), (7, 9, 5), (64, 4, 1)])
 def test_ragged_tiles_and_chunks(gpu_lib, monkeypatch, tx, ty, zc):
     """grids that are not multiples of the tile, many tiles, several z-chunks (edge cases)"""
     monkeypatch.setenv("PFT_TX", str(tx))
@@ -187,8 +187,10 @@ def hr_state(gpu_lib):
 
 
 @pytest.mark.parametrize("env,flags", [
-    ({"PFT_TX": "40", "PFT_TY": "12", "PFT_ZCHUNKS": "7"}, 0),
-    ({"PFT_TX": "100", "PFT_TY": "5", "PFT_ZCHUNKS": "1"}, 0),
+    ({"PFT_TX": "40", "PFT_TY": "6", "PFT_ZCHUNKS": "7"}, 0),
+    ({"PFT_TX": "50", "PFT_TY": "3", "PFT_ZCHUNKS": "1"}, 0),
+    ({"PFT_ROWS2": "1"}, 0),
+    ({"PFT_SPLIT": "1"}, 0),
     ({}, FLAG_FLUX_SHARING),
     ({}, FLAG_LEGACY_LOADS),
     ({}, FLAG_RECOMPUTE_K1 | FLAG_NO_SPECULATION),

@@ -19,7 +19,7 @@ from bench import make_spec, STAGE_BYTES_HEAT, STAGE_BYTES_NOHEAT  # noqa: E402
 
 
 def run(spec, fields, env, flags, attempts, t_h):
-    for k in ("PFT_TX", "PFT_TY", "PFT_ZCHUNKS", "PFT_THREADS", "PFT_PROFILE_STAGES", "PFT_LEGACY", "PFT_SPLIT", "PFT_SHARE"):
+    for k in ("PFT_TX", "PFT_TY", "PFT_ZCHUNKS", "PFT_THREADS", "PFT_PROFILE_STAGES", "PFT_LEGACY", "PFT_SPLIT", "PFT_SHARE", "PFT_ROWS2"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     sol = SlabSolver(spec, flags=flags)
@@ -64,17 +64,16 @@ def main():
     t_h = (s0.sys.t, s0.sys.h)
     s0.close()
     P = {"PFT_PROFILE_STAGES": 1}
-    configs = [({}, 0), ({"PFT_SPLIT": 0}, 0), ({}, 16), (dict(P), 0), ({"PFT_SPLIT": 0, "PFT_PROFILE_STAGES": 1}, 0), ({"PFT_LEGACY": 1}, 0)]
-    tiles = [(100, 5), (50, 10), (50, 5), (50, 4), (50, 3), (100, 3), (40, 6), (26, 10), (20, 12), (50, 8), (50, 6), (100, 4)]
+    configs = [({}, 0), ({"PFT_ROWS2": 1}, 0), (dict(P), 0)]
+    tiles = [(50, 5), (50, 4), (50, 3), (40, 6), (100, 2), (66, 3), (40, 5), (50, 2)]
     if args.quick:
-        tiles = tiles[:6]
+        tiles = tiles[:8]
     for tx, ty in tiles:
         if tx > spec.n1:
             continue
         configs.append(({"PFT_TX": tx, "PFT_TY": ty}, 0))
-        configs.append(({"PFT_TX": tx, "PFT_TY": ty, "PFT_SPLIT": 0}, 0))
     if not args.quick:
-        for tx, ty in ((50, 10), (50, 5)):
+        for tx, ty in ((50, 3), (50, 2)):
             for zc in (4, 8, 16, 37, 74):
                 configs.append(({"PFT_TX": tx, "PFT_TY": ty, "PFT_ZCHUNKS": zc}, 0))
     for env, flags in configs:
