@@ -79,6 +79,7 @@ struct NcclApi {
 	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*GroupStart)(void) = nullptr;
 	ncclResult_t (*GroupEnd)(void) = nullptr;
 	const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -102,6 +103,7 @@ static int nccl_load(void)
 	SYM(Send, "ncclSend")
 	SYM(Recv, "ncclRecv")
 	SYM(AllReduce, "ncclAllReduce")
+	*(void **)(&g_nccl.AllGather) = dlsym(h, "ncclAllGather");      // optional (absent in the CPU test stand-in)
 	SYM(GroupStart, "ncclGroupStart")
 	SYM(GroupEnd, "ncclGroupEnd")
 	SYM(GetErrorString, "ncclGetErrorString")
@@ -141,7 +143,7 @@ struct pft_solver {
 	int model;            // 0,1,2
 	bool heat;
 	bool share;
-	bool speculate;
+	bool speculate, speculate_req;
 	int TX, TY, nzc;
 	dim3 grid, block;
 	size_t smem;
@@ -166,6 +168,17 @@ struct pft_solver {
 	bool profile;
 	std::vector<StageTimer> timers;
 	pft_stats st;
+	// one device slab: [SyncBlock][13 field arrays]; peers map it with CUDA IPC
+	char *slab;
+	size_t slab_bytes;
+	size_t off[A_COUNT][2], off_gl;            // byte offsets of the arrays inside the slab (same on every rank)
+	// peer path (multi-GPU without NCCL in the time loop)
+	bool p2p;
+	char *peer_base[PFT_MAX_RANKS];            // every rank's slab in this process' address space
+	int peer_n3[PFT_MAX_RANKS];
+	unsigned int *halo_tickets;
+	unsigned long long hseq;                   // stage-launch sequence number (identical on all ranks)
+	StageArgs s5_args;                         // argument block of the last stage-5 launch (for eps_allreduce_kernel)
 	// TMA path (heat modes): one tensor map per array, box = tile + halo ring
 	bool use_tma;
 	bool split;           // split-phase mbarriers instead of a CTA barrier per plane
@@ -369,6 +382,33 @@ static cudaError_t launch_stage_tma_t(pft_solver *s, const TmaParams &kp)
 	return s->split ? launch_tma_t<STAGE, 1, false, true>(s, kp) : launch_tma_t<STAGE, 1, false, false>(s, kp);
 }
 
+// peer path: where this launch pushes its boundary planes and whom it signals
+static void fill_peer_args(pft_solver *s, PeerArgs *pr, int out)
+{
+	const int r = s->cs.rank, R = s->cs.nranks;
+	const size_t plane_b = (size_t)s->g.plane * sizeof(double);
+	pr->rank = r; pr->nranks = R;
+	pr->nzc = s->nzc;
+	pr->hseq = ++s->hseq;
+	pr->my_flags = ((SyncBlock *)s->slab)->halo_flag;
+	pr->tickets = s->halo_tickets;
+	pr->wait_lo = (r > 0); pr->wait_hi = (r < R - 1);
+	for (int q = 0; q < R; q++) pr->ranks[q] = (SyncBlock *)s->peer_base[q];
+	if (r > 0) {        // the lower neighbour's UPPER ghost plane (index n3'+1) and its halo_flag[1]
+		char *pb = s->peer_base[r - 1];
+		const size_t gp = (size_t)(s->peer_n3[r - 1] + 1) * plane_b;
+		pr->lo_p = (double *)(pb + s->off[out][1] + gp);
+		pr->lo_u = s->heat ? (double *)(pb + s->off[out][0] + gp) : nullptr;
+		pr->lo_flag = &((SyncBlock *)pb)->halo_flag[1];
+	}
+	if (r < R - 1) {    // the upper neighbour's LOWER ghost plane (index 0) and its halo_flag[0]
+		char *pb = s->peer_base[r + 1];
+		pr->hi_p = (double *)(pb + s->off[out][1]);
+		pr->hi_u = s->heat ? (double *)(pb + s->off[out][0]) : nullptr;
+		pr->hi_flag = &((SyncBlock *)pb)->halo_flag[0];
+	}
+}
+
 // stage launcher: fills the argument block for one Merson stage and (multi-GPU) exchanges the
 // z-boundary planes of what the stage produced
 static int exchange_pair(pft_solver *s, double *u, double *p);
@@ -390,6 +430,7 @@ static int launch_stage(pft_solver *s, int stage, double t_stage, double ha, dou
 	a.ha = ha; a.hb = hb;
 	a.dir_u = dirichlet(s, t_stage);
 	a.cond = cond;
+	if (s->p2p) fill_peer_args(s, &a.pr, out);
 	if (stage == 5) {
 		a.delta = sys->delta; a.h_abs = h_abs; a.h_min = sys->h_min;
 		a.eps_scale = eps_scale; a.scale_eps = sys->delta_local ? 1 : 0;
@@ -397,6 +438,7 @@ static int launch_stage(pft_solver *s, int stage, double t_stage, double ha, dou
 		a.ctl = s->ctl; a.slot = s->slot_dev; a.seq = ++s->seq;
 		a.nblocks = s->grid.x * s->grid.y * s->grid.z;
 	}
+	if (stage == 5) s->s5_args = a;
 	StageTimer tm{};
 	if (s->profile) {
 		cudaEventCreate(&tm.a); cudaEventCreate(&tm.b); tm.stage = stage;
@@ -434,7 +476,7 @@ static int launch_stage(pft_solver *s, int stage, double t_stage, double ha, dou
 	if (s->profile) { cudaEventRecord(tm.b, s->stream); s->timers.push_back(tm); }
 	s->st.kernel_launches++;
 	s->st.stage_launches[stage - 1]++;
-	if (s->cs.nranks > 1) {
+	if (s->cs.nranks > 1 && !s->p2p) {
 		int rc = exchange_pair(s, s->heat ? s->arr[out][0] : nullptr, s->arr[out][1]);
 		if (rc) return rc;
 	}
@@ -492,6 +534,68 @@ extern "C" int pft_comm_unique_id(void *id128)
 	return 0;
 }
 
+// slab depth of rank r: apps/intertrack-hybrid-S-freezing/intertrack.c:1780-1787
+static int slab_n3(int total_n3, int nranks, int r)
+{
+	return total_n3 / nranks + (r < total_n3 % nranks ? 1 : 0);
+}
+
+// Peer path: every rank exports its slab with CUDA IPC, the handles travel once through the NCCL
+// communicator, and from then on the time loop contains no collective call at all: boundary planes
+// are stored straight into the neighbours' ghost planes by the stage kernels, flags and the
+// per-slab error maxima travel as peer stores (pft_kernels.cuh, "peer-memory halo exchange").
+static int setup_p2p(pft_solver *s)
+{
+	const int R = s->cs.nranks, r = s->cs.rank;
+	if (R > PFT_MAX_RANKS) return fail(PFT_EINVAL, "peer path supports at most %d ranks", PFT_MAX_RANKS);
+	struct Export { cudaIpcMemHandle_t h; int n3; int ok; unsigned long long bytes; };
+	Export mine;
+	memset(&mine, 0, sizeof mine);
+	mine.ok = (cudaIpcGetMemHandle(&mine.h, s->slab) == cudaSuccess);
+	if (!mine.ok) cudaGetLastError();
+	mine.n3 = s->cs.n3;
+	mine.bytes = s->slab_bytes;
+	Export *d = nullptr;
+	std::vector<Export> all(R);
+	CU(cudaMalloc(&d, sizeof(Export) * R));
+	CU(cudaMemcpyAsync(d + r, &mine, sizeof mine, cudaMemcpyHostToDevice, s->stream));
+	NC(g_nccl.AllGather(d + r, d, sizeof(Export), ncclInt8, s->comm, s->stream));
+	CU(cudaMemcpyAsync(all.data(), d, sizeof(Export) * R, cudaMemcpyDeviceToHost, s->stream));
+	CU(cudaStreamSynchronize(s->stream));
+	cudaFree(d);
+	bool ok = true;
+	for (int q = 0; q < R; q++) {
+		ok = ok && all[q].ok && all[q].bytes == s->slab_bytes;
+		if (all[q].n3 != slab_n3(s->cs.total_n3, R, q)) return fail(PFT_EINVAL, "rank %d holds %d planes, expected %d", q, all[q].n3, slab_n3(s->cs.total_n3, R, q));
+		s->peer_n3[q] = all[q].n3;
+	}
+	if (ok) {
+		for (int q = 0; q < R && ok; q++) {
+			if (q == r) { s->peer_base[q] = s->slab; continue; }
+			void *p = nullptr;
+			cudaError_t e = cudaIpcOpenMemHandle(&p, all[q].h, cudaIpcMemLazyEnablePeerAccess);
+			if (e != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+			s->peer_base[q] = (char *)p;
+		}
+	}
+	// every rank must take the same path: agree through the communicator
+	double flag = ok ? 1.0 : 0.0, *df = nullptr;
+	CU(cudaMalloc(&df, sizeof(double)));
+	CU(cudaMemcpyAsync(df, &flag, sizeof flag, cudaMemcpyHostToDevice, s->stream));
+	NC(g_nccl.AllReduce(df, df, 1, ncclDouble, ncclMin, s->comm, s->stream));
+	CU(cudaMemcpyAsync(&flag, df, sizeof flag, cudaMemcpyDeviceToHost, s->stream));
+	CU(cudaStreamSynchronize(s->stream));
+	cudaFree(df);
+	s->p2p = (flag == 1.0);
+	if (!s->p2p)
+		for (int q = 0; q < R; q++) {
+			if (s->peer_base[q] && s->peer_base[q] != s->slab) cudaIpcCloseMemHandle(s->peer_base[q]);
+			s->peer_base[q] = nullptr;
+		}
+	s->speculate = s->speculate_req && (s->cs.nranks == 1 || s->p2p);
+	return 0;
+}
+
 extern "C" int pft_comm_init(pft_solver *s, const void *id128)
 {
 	if (!s || !id128) return fail(PFT_EINVAL, "null argument");
@@ -503,6 +607,11 @@ extern "C" int pft_comm_init(pft_solver *s, const void *id128)
 	memcpy(&id, id128, sizeof id);
 	NC(g_nccl.CommInitRank(&s->comm, s->cs.nranks, id, s->cs.rank));
 	s->have_comm = true;
+	const char *mode = getenv("PFT_COMM");       // "p2p" (default) | "nccl"
+	if (!(mode && !strcmp(mode, "nccl")) && g_nccl.AllGather) {
+		rc = setup_p2p(s);
+		if (rc) return rc;
+	}
 	return 0;
 }
 
@@ -539,7 +648,8 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	// Sharing face fluxes through shared memory saves ~25% of the fp64 work but costs a second CTA
 	// barrier per plane; measured on B200 it loses (profiles/round1_tuning.md), so it is opt-in.
 	s->share = s->heat && !(flags & PFT_FLAG_NO_FLUX_SHARING) && ((flags & PFT_FLAG_FLUX_SHARING) || env_int("PFT_SHARE", 0));
-	s->speculate = !(flags & PFT_FLAG_NO_SPECULATION) && !env_int("PFT_NO_SPECULATION", 0) && cs->nranks == 1;
+	s->speculate_req = !(flags & PFT_FLAG_NO_SPECULATION) && !env_int("PFT_NO_SPECULATION", 0);
+	s->speculate = s->speculate_req && cs->nranks == 1;      // N > 1: enabled by the peer path (setup_p2p)
 	s->profile = env_int("PFT_PROFILE_STAGES", 0) != 0;
 	make_consts(s);
 
@@ -549,7 +659,9 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	g.plane = (long long)g.px * cs->n2;
 	g.front = (cs->rank == 0);
 	g.rear = (cs->rank == cs->nranks - 1);
-	s->field = g.plane * (cs->n3 + 2);
+	// every rank sizes its arrays for the deepest slab so that array offsets inside the slab are
+	// the same on all ranks (peers address each other's arrays by offset)
+	s->field = g.plane * ((cs->total_n3 + cs->nranks - 1) / cs->nranks + 2);
 	s->N1 = cs->n1 + 2 * PFT_BT; s->N2 = cs->n2 + 2 * PFT_BT; s->N3 = cs->n3 + 2 * PFT_BT;
 	s->padded = (long long)PFT_NVAR * s->N1 * s->N2 * s->N3;
 
@@ -588,20 +700,29 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 	CU(cudaEventCreate(&s->ev0)); CU(cudaEventCreate(&s->ev1));
 	CU(cudaEventCreateWithFlags(&s->ev_red, cudaEventDisableTiming));
-	const size_t fb = (size_t)s->field * sizeof(double);
-	for (int a = 0; a < A_COUNT; a++)
-		for (int q = 0; q < 2; q++) {
-			// calc_mode 10/11: du/dt == 0 (equation.c:708), so u is static: no K/aux arrays for it,
-			// and the candidate state shares the one temperature array
-			if (!s->heat && q == 0 && a != A_X) { s->arr[a][q] = nullptr; continue; }
-			e = cudaMalloc(&s->arr[a][q], fb);
-			if (e != cudaSuccess) { pft_destroy(s); return fail(PFT_ENOMEM, "cudaMalloc(%zu): %s", fb, cudaGetErrorString(e)); }
-			CU(cudaMemsetAsync(s->arr[a][q], 0, fb, s->stream));
-		}
-	e = cudaMalloc(&s->gl, fb);
-	if (e != cudaSuccess) { pft_destroy(s); return fail(PFT_ENOMEM, "cudaMalloc(%zu): %s", fb, cudaGetErrorString(e)); }
-	CU(cudaMemsetAsync(s->gl, 0, fb, s->stream));
-	if (!s->heat) s->arr[A_XN][0] = s->arr[A_X][0];
+	const size_t fb = ((size_t)s->field * sizeof(double) + 255) & ~(size_t)255;
+	{
+		// layout: identical on every rank of a run with equal slab depth; offsets are exchanged anyway
+		size_t off = (sizeof(SyncBlock) + 255) & ~(size_t)255;
+		for (int a = 0; a < A_COUNT; a++)
+			for (int q = 0; q < 2; q++) {
+				// calc_mode 10/11: du/dt == 0 (equation.c:708), so u is static: no K/aux arrays for it,
+				// and the candidate state shares the one temperature array
+				if (!s->heat && q == 0 && a != A_X) { s->off[a][q] = 0; continue; }
+				s->off[a][q] = off; off += fb;
+			}
+		s->off_gl = off; off += fb;
+		s->slab_bytes = off;
+		e = cudaMalloc(&s->slab, s->slab_bytes);
+		if (e != cudaSuccess) { s->slab = nullptr; pft_destroy(s); return fail(PFT_ENOMEM, "cudaMalloc(%zu): %s", s->slab_bytes, cudaGetErrorString(e)); }
+		CU(cudaMemsetAsync(s->slab, 0, s->slab_bytes, s->stream));
+		for (int a = 0; a < A_COUNT; a++)
+			for (int q = 0; q < 2; q++) s->arr[a][q] = s->off[a][q] ? (double *)(s->slab + s->off[a][q]) : nullptr;
+		s->gl = (double *)(s->slab + s->off_gl);
+		if (!s->heat) { s->arr[A_XN][0] = s->arr[A_X][0]; s->off[A_XN][0] = s->off[A_X][0]; }
+	}
+	CU(cudaMalloc(&s->halo_tickets, 2 * sizeof(unsigned int)));
+	CU(cudaMemsetAsync(s->halo_tickets, 0, 2 * sizeof(unsigned int), s->stream));
 
 	s->split = s->use_tma && !s->share && env_int("PFT_SPLIT", 0) != 0;
 	if (s->use_tma) {
@@ -649,9 +770,10 @@ extern "C" int pft_destroy(pft_solver *s)
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	drain_timers(s);
 	if (s->have_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
-	if (!s->heat) s->arr[A_XN][0] = nullptr;      // alias of arr[A_X][0]
-	for (int a = 0; a < A_COUNT; a++) for (int q = 0; q < 2; q++) if (s->arr[a][q]) cudaFree(s->arr[a][q]);
-	if (s->gl) cudaFree(s->gl);
+	for (int r = 0; r < PFT_MAX_RANKS; r++)
+		if (s->peer_base[r] && s->peer_base[r] != s->slab) cudaIpcCloseMemHandle(s->peer_base[r]);
+	if (s->slab) cudaFree(s->slab);
+	if (s->halo_tickets) cudaFree(s->halo_tickets);
 	if (s->stage_buf) cudaFree(s->stage_buf);
 	if (s->ctl) cudaFree(s->ctl);
 	if (s->red) cudaFree(s->red);
@@ -943,13 +1065,17 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 		const unsigned long long seq = s->seq;
 
 		double eps; int nonfinite;
-		if (!multi) {
+		if (!multi || s->p2p) {
+			if (s->p2p) {      // device-side global max + decision: the role of MPI_Allreduce(MAX), :572
+				PFT_LAUNCH(eps_allreduce_kernel, dim3(1), dim3(32), 0, s->stream, s->s5_args, (SyncBlock *)s->slab);
+				s->st.kernel_launches++;
+			}
 			if (s->speculate)          // K1 of the next step, gated on the device-side accept flag
 				if ((rc = launch_stage(s, 1, t + h, 0.0, 0.0, xn, A_K1, &s->ctl->accept, sys, 0.0, 1.0))) goto device_error;
 			if ((rc = wait_slot(s, seq))) goto device_error;
 			eps = s->slot->eps; nonfinite = s->slot->nonfinite;
 		} else {
-			// global max over the slabs: the role of MPI_Allreduce(MAX), :572
+			// NCCL path (PFT_COMM=nccl, or no peer access): global max over the slabs through the host
 			if ((rc = wait_slot(s, seq))) goto device_error;
 			s->red_host[0] = s->slot->eps; s->red_host[1] = (double)s->slot->nonfinite;
 			if (cudaMemcpyAsync(s->red, s->red_host, 2 * sizeof(double), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) { rc = fail(PFT_ECUDA, "memcpy"); goto device_error; }
@@ -978,7 +1104,7 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 			command |= CMD_UPDATE;
 			if (fabs(final_time - (t + h)) <= fabs(new_h)) command |= CMD_NEXTFINISH;
 		}
-		if (!multi) {
+		if (!multi || s->p2p) {
 			const int host_accept = ((command & CMD_UPDATE) && !(command & CMD_NAN)) ? 1 : 0;
 			if (host_accept != s->slot->accept) {
 				rc = fail(PFT_ESTATE, "device/host acceptance mismatch (eps %.17g delta %.17g h %.17g)", eps, delta, h);
@@ -1000,7 +1126,7 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 				t += h;
 				std::swap(xc, xn);
 				sys->steps++; s->st.accepted++;
-				if (!multi && s->speculate) { sys->rhs_evals++; s->st.rhs_evals++; }     // the gated stage 1 ran
+				if ((!multi || s->p2p) && s->speculate) { sys->rhs_evals++; s->st.rhs_evals++; }     // the gated stage 1 ran
 				else {
 					if ((rc = launch_stage(s, 1, t, 0.0, 0.0, xc, A_K1, nullptr, sys, 0.0, 1.0))) goto device_error;
 					sys->rhs_evals++; s->st.rhs_evals++;
@@ -1051,6 +1177,8 @@ done:
 		std::swap(s->arr[A_X][1], s->arr[A_XN][1]);
 		std::swap(s->tmap[A_X][0], s->tmap[A_XN][0]);
 		std::swap(s->tmap[A_X][1], s->tmap[A_XN][1]);
+		std::swap(s->off[A_X][0], s->off[A_XN][0]);
+		std::swap(s->off[A_X][1], s->off[A_XN][1]);
 	}
 	return ret;
 

@@ -78,7 +78,40 @@ struct HostSlot {
 	int nonfinite;
 };
 
+constexpr int PFT_MAX_RANKS = 16;
+
+// one rank's local error maximum of an attempt, as seen by every rank (peer-written)
+struct EpsSlot {
+	unsigned long long seq;
+	double eps;
+	int nonfinite, pad;
+	unsigned long long pad2;
+};
+
+// head of every rank's device slab; peers map it through CUDA IPC
+struct SyncBlock {
+	unsigned long long halo_flag[2];     // [0] written by the lower neighbour, [1] by the upper: stage sequence numbers
+	unsigned long long pad[2];
+	EpsSlot slot[2][PFT_MAX_RANKS];      // [attempt & 1][rank]
+};
+
+// peer-memory halo exchange (one process per GPU, slabs mapped into each other with CUDA IPC);
+// all zero on a single GPU and on the NCCL path
+struct PeerArgs {
+	double *lo_u, *lo_p;                 // lower neighbour's upper ghost plane of this stage's output pair
+	double *hi_u, *hi_p;                 // upper neighbour's lower ghost plane
+	unsigned long long *lo_flag, *hi_flag;   // the neighbours' halo_flag entries this rank signals
+	const unsigned long long *my_flags;  // this rank's halo_flag[2]
+	unsigned int *tickets;               // finished boundary CTAs, [lower, upper]
+	unsigned long long hseq;             // sequence number of this stage launch (identical on every rank)
+	SyncBlock *ranks[PFT_MAX_RANKS];     // stage 5: every rank's sync block (error-max broadcast)
+	int rank, nranks;
+	int wait_lo, wait_hi;                // this slab has a lower / an upper neighbour
+	int nzc;                             // number of z-chunks (boundary chunks are scheduled first)
+};
+
 struct StageArgs {
+	PeerArgs pr;
 	const double *xu, *xp, *gl;                 // step-start state (u, p) and the static glass field
 	const double *k1u, *k1p, *k3u, *k3p, *k4u, *k4p;
 	const double *au, *ap;                      // stage 3: the stored stage input (aux3)
@@ -191,6 +224,84 @@ __device__ __forceinline__ void load_state(const StageArgs &a, long long idx, do
 
 // ----------------------------------------------------------------------------------------
 
+// ----------------------------------------------------------------------------------------
+// peer-memory halo exchange protocol
+//
+//  * boundary-chunk CTAs of stage launch n first wait until the neighbour's flag shows n-1: the
+//    neighbour's boundary CTAs finished launch n-1, i.e. its pushes into OUR ghost planes have
+//    landed (RAW) and it no longer reads ITS ghost planes of launch n-1 (WAR for our pushes);
+//  * they store their output planes k = 0 / n3-1 also into the neighbour's ghost planes;
+//  * the last boundary CTA of a side (ticket) publishes flag = n to that neighbour.
+// Flags are monotonic, launches are identical on every rank.  Interior CTAs never wait.
+
+#ifndef PFT_CUDA_EMU
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+#else
+inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return *p; }
+inline void st_release_sys(unsigned long long *p, unsigned long long v) { *p = v; }
+#endif
+
+// chunk processed by this CTA: the two boundary chunks come first in launch order, so that
+// their planes reach the neighbours while the interior is still being computed
+__device__ __forceinline__ int chunk_of_block(int nzc)
+{
+	const int z = blockIdx.z;
+	if (nzc < 3) return z;
+	return z == 0 ? 0 : (z == 1 ? nzc - 1 : z - 1);
+}
+
+__device__ __forceinline__ void halo_wait(const PeerArgs &pr, bool lo, bool hi, int tid)
+{
+	const bool wl = lo && pr.wait_lo, wh = hi && pr.wait_hi;
+	if (!(wl || wh)) return;
+	if (tid == 0) {
+		if (wl) while (ld_acquire_sys(&pr.my_flags[0]) + 1 < pr.hseq) { }
+		if (wh) while (ld_acquire_sys(&pr.my_flags[1]) + 1 < pr.hseq) { }
+	}
+	__syncthreads();
+}
+
+__device__ __forceinline__ void halo_signal(const PeerArgs &pr, bool lo, bool hi, int tid)
+{
+	const bool wl = lo && pr.wait_lo, wh = hi && pr.wait_hi;
+	if (!(wl || wh)) return;
+	__threadfence_system();              // this thread's peer stores are visible system-wide ...
+	__syncthreads();                     // ... for every thread of the CTA, before it is counted
+	if (tid == 0) {
+		const unsigned int n = gridDim.x * gridDim.y;
+		if (wl && atomicAdd(&pr.tickets[0], 1u) == n - 1) { pr.tickets[0] = 0u; __threadfence_system(); st_release_sys(pr.lo_flag, pr.hseq); }
+		if (wh && atomicAdd(&pr.tickets[1], 1u) == n - 1) { pr.tickets[1] = 0u; __threadfence_system(); st_release_sys(pr.hi_flag, pr.hseq); }
+	}
+}
+
+// a skipped launch (speculative stage 1 of a rejected step) still has to advance the flags
+__device__ __forceinline__ void halo_skip(const PeerArgs &pr)
+{
+	if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0) {
+		if (pr.wait_lo) st_release_sys(pr.lo_flag, pr.hseq);
+		if (pr.wait_hi) st_release_sys(pr.hi_flag, pr.hseq);
+	}
+}
+
+// store one output pair value, and push it into the neighbours' ghost planes from the boundary planes
+template <bool HEAT>
+__device__ __forceinline__ void store_out(const StageArgs &a, long long o, long long col, int k, int n3, double vu, double vp)
+{
+	a.op[o] = vp;
+	if (HEAT) a.ou[o] = vu;
+	if (k == 0 && a.pr.lo_p) { a.pr.lo_p[col] = vp; if (HEAT) a.pr.lo_u[col] = vu; }
+	if (k == n3 - 1 && a.pr.hi_p) { a.pr.hi_p[col] = vp; if (HEAT) a.pr.hi_u[col] = vu; }
+}
+
 // ---- stage 5 epilogue: grid-wide max of the error estimate, acceptance decision, host notification
 __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, double emax, int nonfinite)
 {
@@ -217,10 +328,23 @@ __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, doubl
 			double ecmp = a.scale_eps ? eps * a.eps_scale : eps;            // RK_MPI_SAsolver_hybrid2.c:578
 			int acc = (ecmp < a.delta) || (a.h_abs < a.h_min);               // :599
 			if (a.handle_nan && nfl) acc = 0;                                 // :626-646
-			ctl->accept = acc;
 			ctl->eps_bits = 0ull;
 			ctl->nonfinite = 0;
 			ctl->ticket = 0u;
+			if (a.pr.nranks > 1) {
+				// peer path: hand this slab's maximum to every rank; eps_allreduce_kernel (next in
+				// every rank's stream) forms the global maximum and the decision
+				const int b = (int)(a.seq & 1ull);
+				for (int r = 0; r < a.pr.nranks; r++) {
+					EpsSlot *e = &a.pr.ranks[r]->slot[b][a.pr.rank];
+					e->eps = eps;
+					e->nonfinite = nfl;
+				}
+				__threadfence_system();
+				for (int r = 0; r < a.pr.nranks; r++) st_release_sys(&a.pr.ranks[r]->slot[b][a.pr.rank].seq, a.seq);
+				return;
+			}
+			ctl->accept = acc;
 			__threadfence();
 			HostSlot *s = a.slot;
 			s->eps = eps;
@@ -243,7 +367,7 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 	const Geom &g = P.g;
 	const StageArgs &a = P.a;
 
-	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) return; }
+	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) { halo_skip(a.pr); return; } }
 
 	constexpr int NF = HEAT ? 3 : 1;        // fields kept in the shared tile: p [, u, gl]
 	constexpr bool FLUX = HEAT && SHARE;
@@ -265,8 +389,10 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 	const int ic = min(i, g.n1 - 1), jc = min(j, g.n2 - 1);
 	const long long col = (long long)jc * g.px + ic;        // in-plane offset of this thread's column
 
-	const int k0 = blockIdx.z * g.zc;
+	const int k0 = chunk_of_block(a.pr.nzc) * g.zc;
 	const int k1 = min(g.n3, k0 + g.zc);
+	const bool chunk_lo = (k0 == 0), chunk_hi = (k1 == g.n3);
+	halo_wait(a.pr, chunk_lo, chunk_hi, ty * blockDim.x + tx);
 
 	// halo-ring duty: the first 2*TX+2*TY threads each fetch one ring cell per plane
 	const int nh = 2 * TX + 2 * TY;
@@ -415,22 +541,24 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 		if (active) {
 			const long long o = (long long)(k + 1) * g.plane + col;
 			if (STAGE == 1 || STAGE == 3 || STAGE == 4) {
-				a.op[o] = dp;
-				if (HEAT) a.ou[o] = du;
+				store_out<HEAT>(a, o, col, k, g.n3, du, dp);
 			} else if (STAGE == 2) {
-				a.op[o] = (rc.k1p + dp) * a.hb + rc.xp;                                   // :408
-				if (HEAT) a.ou[o] = (rc.k1u + du) * a.hb + rc.xu;
+				const double vp = (rc.k1p + dp) * a.hb + rc.xp;                               // :408
+				const double vu = HEAT ? (rc.k1u + du) * a.hb + rc.xu : 0.0;
+				store_out<HEAT>(a, o, col, k, g.n3, vu, vp);
 			} else {
 				double e = fabs(0.2 * rc.k1p - 0.9 * rc.k3p + 0.8 * rc.k4p - 0.1 * dp);   // :521
 				if (!(e <= 1.7976931348623157e308)) nonfinite = 1;
 				emax = (e > emax) ? e : emax;
-				a.op[o] = rc.xp + a.hb * (0.5 * (rc.k1p + dp) + 2.0 * rc.k4p);            // :667
+				const double vp = rc.xp + a.hb * (0.5 * (rc.k1p + dp) + 2.0 * rc.k4p);        // :667
+				double vu = 0.0;
 				if (HEAT) {
 					double eu = fabs(0.2 * rc.k1u - 0.9 * rc.k3u + 0.8 * rc.k4u - 0.1 * du);
 					if (!(eu <= 1.7976931348623157e308)) nonfinite = 1;
 					emax = (eu > emax) ? eu : emax;
-					a.ou[o] = rc.xu + a.hb * (0.5 * (rc.k1u + du) + 2.0 * rc.k4u);
+					vu = rc.xu + a.hb * (0.5 * (rc.k1u + du) + 2.0 * rc.k4u);
 				}
+				store_out<HEAT>(a, o, col, k, g.n3, vu, vp);
 			}
 		}
 
@@ -450,7 +578,46 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 		cur ^= 1;
 	}
 
+	halo_signal(a.pr, chunk_lo, chunk_hi, tid);
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
+}
+
+// global maximum of the per-slab error estimates + the acceptance decision (peer path): one
+// warp, lane r waits for rank r's slot of this attempt.  Plays the role of MPI_Allreduce(MAX)
+// (RK_MPI_SAsolver_hybrid2.c:572) without leaving the device.
+__global__ void eps_allreduce_kernel(StageArgs a, SyncBlock *mine)
+{
+	const int r = threadIdx.x;
+	const int b = (int)(a.seq & 1ull);
+	double eps = 0.0;
+	int nf = 0;
+	if (r < a.pr.nranks) {
+		const EpsSlot *e = &mine->slot[b][r];
+		while (ld_acquire_sys(&e->seq) != a.seq) { }
+		eps = *(volatile const double *)&e->eps;
+		nf = *(volatile const int *)&e->nonfinite;
+	}
+#ifndef PFT_CUDA_EMU
+	for (int o = 16; o > 0; o >>= 1) {
+		double w = __shfl_xor_sync(0xffffffffu, eps, o);
+		eps = (w > eps) ? w : eps;
+		nf |= __shfl_xor_sync(0xffffffffu, nf, o);
+	}
+#endif
+	if (r == 0) {
+		double ecmp = a.scale_eps ? eps * a.eps_scale : eps;            // RK_MPI_SAsolver_hybrid2.c:578
+		int acc = (ecmp < a.delta) || (a.h_abs < a.h_min);               // :599
+		if (a.handle_nan && nf) acc = 0;                                  // :626-646
+		a.ctl->accept = acc;
+		__threadfence();
+		HostSlot *s = a.slot;
+		s->eps = eps;
+		s->accept = acc;
+		s->nonfinite = nf;
+		__threadfence_system();
+		*(volatile unsigned long long *)&s->seq = a.seq;
+		__threadfence_system();
+	}
 }
 
 // ----------------------------------------------------------------------------------------

@@ -157,14 +157,14 @@ __device__ __forceinline__ void cell_rhs(const Consts &c, double uc, double pc, 
 // the fused combination that follows stage STAGE, for one cell (operands from the raw buffer)
 template <int STAGE>
 __device__ __forceinline__ void stage_output(const StageArgs &a, const double *rb, int AS, int IU, int cs, long long o,
-                                             double du, double dp, double &emax, int &nonfinite)
+                                             long long col, int k, int n3, double du, double dp, double &emax, int &nonfinite)
 {
 	if (STAGE == 1 || STAGE == 3 || STAGE == 4) {
-		a.op[o] = dp;
-		a.ou[o] = du;
+		store_out<true>(a, o, col, k, n3, du, dp);
 	} else if (STAGE == 2) {
-		a.op[o] = (rb[AS + cs] + dp) * a.hb + rb[cs];                                           // hybrid2.c:408
-		a.ou[o] = (rb[(IU + 1) * AS + cs] + du) * a.hb + rb[IU * AS + cs];
+		const double vp = (rb[AS + cs] + dp) * a.hb + rb[cs];                                   // hybrid2.c:408
+		const double vu = (rb[(IU + 1) * AS + cs] + du) * a.hb + rb[IU * AS + cs];
+		store_out<true>(a, o, col, k, n3, vu, vp);
 	} else {
 		const double xp = rb[cs], k1p = rb[AS + cs], k3p = rb[2 * AS + cs], k4p = rb[3 * AS + cs];
 		const double xu = rb[IU * AS + cs], k1u = rb[(IU + 1) * AS + cs], k3u = rb[(IU + 2) * AS + cs], k4u = rb[(IU + 3) * AS + cs];
@@ -173,8 +173,9 @@ __device__ __forceinline__ void stage_output(const StageArgs &a, const double *r
 		if (!(e <= 1.7976931348623157e308) || !(eu <= 1.7976931348623157e308)) nonfinite = 1;
 		emax = (e > emax) ? e : emax;
 		emax = (eu > emax) ? eu : emax;
-		a.op[o] = xp + a.hb * (0.5 * (k1p + dp) + 2.0 * k4p);                                   // :667
-		a.ou[o] = xu + a.hb * (0.5 * (k1u + du) + 2.0 * k4u);
+		const double vp = xp + a.hb * (0.5 * (k1p + dp) + 2.0 * k4p);                           // :667
+		const double vu = xu + a.hb * (0.5 * (k1u + du) + 2.0 * k4u);
+		store_out<true>(a, o, col, k, n3, vu, vp);
 	}
 }
 
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 	const Geom &g = P.g;
 	const StageArgs &a = P.a;
 
-	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) return; }
+	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) { halo_skip(a.pr); return; } }
 
 	constexpr int NP = stage_np(STAGE);
 	constexpr int NA = 2 * NP + 1;
@@ -227,8 +228,9 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 	const int sS = (j > 0) ? cs - BX : cs;
 	const int sN = (j < g.n2 - 1) ? cs + BX : cs;
 
-	const int k0 = blockIdx.z * g.zc;
+	const int k0 = chunk_of_block(a.pr.nzc) * g.zc;
 	const int k1 = min(g.n3, k0 + g.zc);
+	const bool chunk_lo = (k0 == 0), chunk_hi = (k1 == g.n3);
 	// chunk-local plane index q: z = k0 - 1 + q, array plane index = k0 + q
 	const int qlo = (k0 == 0 && g.front) ? 1 : 0;                    // z-front mirror: plane -1 is never fetched
 	const int qhi = (k1 == g.n3 && g.rear) ? (k1 - k0) : (k1 - k0 + 1);   // z-rear ghost is Dirichlet/mirror
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 		fence_mbar_init();
 	}
 	__syncthreads();
+	halo_wait(a.pr, chunk_lo, chunk_hi, tid);     // peer path: the neighbours' planes of the previous launch have landed
 
 	// thread 0 requests plane q into raw buffer b: one tensor copy per array
 	const uint32_t plane_bytes = (uint32_t)(NA * BX * P.by * sizeof(double));
@@ -378,8 +381,8 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 
 		// ---- fused combination that follows this stage (operands re-read from the raw buffer)
 		if (active) {
-			const long long o = (long long)(k + 1) * g.plane + (long long)j * g.px + i;
-			stage_output<STAGE>(a, rb, AS, IU, cs, o, du, dp, emax, nonfinite);
+			const long long col = (long long)j * g.px + i;
+			stage_output<STAGE>(a, rb, AS, IU, cs, (long long)(k + 1) * g.plane + col, col, k, g.n3, du, dp, emax, nonfinite);
 		}
 
 		// ---- this plane is done: raw[bq] may be refilled, tile[tc] overwritten (two planes later)
@@ -391,6 +394,7 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 		if (FORM) { tc = tn; tn = (tn + 1 == NT) ? 0 : tn + 1; }
 	}
 
+	halo_signal(a.pr, chunk_lo, chunk_hi, tid);
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
 }
 
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(256, 2) merson_stage_tma2(const __grid_constan
 	const Geom &g = P.g;
 	const StageArgs &a = P.a;
 
-	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) return; }
+	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) { halo_skip(a.pr); return; } }
 
 	constexpr int NP = stage_np(STAGE);
 	constexpr int NA = 2 * NP + 1;
@@ -434,8 +438,9 @@ __global__ void __launch_bounds__(256, 2) merson_stage_tma2(const __grid_constan
 	const int sS = (jA > 0) ? csA - BX : csA;                        // below A
 	const int sN = (jB < g.n2 - 1) ? csB + BX : csB;                 // above B
 
-	const int k0 = blockIdx.z * g.zc;
+	const int k0 = chunk_of_block(a.pr.nzc) * g.zc;
 	const int k1 = min(g.n3, k0 + g.zc);
+	const bool chunk_lo = (k0 == 0), chunk_hi = (k1 == g.n3);
 	const int qlo = (k0 == 0 && g.front) ? 1 : 0;
 	const int qhi = (k1 == g.n3 && g.rear) ? (k1 - k0) : (k1 - k0 + 1);
 
@@ -464,6 +469,7 @@ __global__ void __launch_bounds__(256, 2) merson_stage_tma2(const __grid_constan
 		fence_mbar_init();
 	}
 	__syncthreads();
+	halo_wait(a.pr, chunk_lo, chunk_hi, tid);     // peer path: the neighbours' planes of the previous launch have landed
 
 	const uint32_t plane_bytes = (uint32_t)(NA * BX * P.by * sizeof(double));
 	auto issue = [&](int q, int b) {
@@ -567,9 +573,10 @@ __global__ void __launch_bounds__(256, 2) merson_stage_tma2(const __grid_constan
 		cell_rhs<MODEL>(c, ucA, pcA, gcA, pwA, peA, psA, pUp, pmA, pnA, sumA, duA, dpA);
 		cell_rhs<MODEL>(c, ucB, pcB, gcB, pwB, peB, pcA, pnB_, pmB, pnB, sumB, duB, dpB);
 
-		const long long oA = (long long)(k + 1) * g.plane + (long long)jA * g.px + i;
-		if (actA) stage_output<STAGE>(a, rb, AS, IU, csA, oA, duA, dpA, emax, nonfinite);
-		if (actB) stage_output<STAGE>(a, rb, AS, IU, csB, oA + g.px, duB, dpB, emax, nonfinite);
+		const long long colA = (long long)jA * g.px + i;
+		const long long oA = (long long)(k + 1) * g.plane + colA;
+		if (actA) stage_output<STAGE>(a, rb, AS, IU, csA, oA, colA, k, g.n3, duA, dpA, emax, nonfinite);
+		if (actB) stage_output<STAGE>(a, rb, AS, IU, csB, oA + g.px, colA + g.px, k, g.n3, duB, dpB, emax, nonfinite);
 
 		__syncthreads();
 		umA = ucA; pmA = pcA; gmA = gcA; ucA = unA; pcA = pnA; gcA = gnA;
@@ -578,6 +585,7 @@ __global__ void __launch_bounds__(256, 2) merson_stage_tma2(const __grid_constan
 		{ const int t = bq; bq = bn; bn = bf; bf = t; }
 	}
 
+	halo_signal(a.pr, chunk_lo, chunk_hi, tid);
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
 }
 

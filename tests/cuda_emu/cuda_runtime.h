@@ -108,6 +108,11 @@ template <class T> static inline cudaError_t cudaHostGetDevicePointer(T **d, voi
 static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return 1; }       // no peers on a CPU
+static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return 1; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 enum { cudaEnableDefault = 0 };
 typedef int cudaDriverEntryPointQueryResult;
 enum { cudaDriverEntryPointSuccess = 0 };

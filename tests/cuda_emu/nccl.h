@@ -7,5 +7,5 @@
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef enum { ncclSuccess = 0, ncclInternalError = 3 } ncclResult_t;
-typedef enum { ncclInt8 = 0, ncclInt32 = 2, ncclFloat64 = 8, ncclDouble = 8 } ncclDataType_t;
+typedef enum { ncclInt8 = 0, ncclChar = 0, ncclInt32 = 2, ncclFloat64 = 8, ncclDouble = 8 } ncclDataType_t;
 typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
