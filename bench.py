@@ -46,6 +46,18 @@ def peaks():
 
 
 def make_spec(name: str, nranks: int):
+    if name.startswith("params:"):
+        # any reference `Params` case file, through the front end of porousfreezethaw_b200/params.py
+        from porousfreezethaw_b200 import params as pfront
+        spec, pc = pfront.case_from_params(name[7:])
+        sph = os.path.join(os.path.dirname(os.path.abspath(name[7:])), "data", "spheres_positions.txt")
+        if not os.path.exists(sph):
+            sph = os.path.join(ROOT, "oracle", "_ref", "data", "spheres_positions.txt")
+        spec.spheres = np.loadtxt(sph).reshape(-1, 3) if os.path.exists(sph) else cases.synthetic_spheres(200, zmax=1.6)
+        u, p, gl = pfront.initial_fields_from_formulas(spec, pc.icond)
+        spec.initial_fields = lambda first_row=0, n3_local=None, _f=(u, p, gl), _s=spec: tuple(
+            a[first_row:first_row + (_s.n3 if n3_local is None else n3_local)] for a in _f)
+        return spec, "strong", f"case file {name[7:]}"
     if name.startswith("cube-"):
         # cube-400 | cube-800 (strong scaling) | cube-800w (weak: 800x800x(100*N))
         tag = name[5:]
