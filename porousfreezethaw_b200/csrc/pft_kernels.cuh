@@ -674,7 +674,10 @@ __global__ void rasterise_kernel(double *gl, const double *bx, const double *by,
 	const long long ic = (long long)(k + 1) * plane + (long long)j * px + i;
 	double v = valid ? gl[ic] : 0.0;
 	const double s = 0.5 / xi_gl;
-	// a sphere further than R + 40*xi_gl contributes < 1e-17: skip its tanh (result-neutral below 1 ulp of 1)
+	// tanh(a) rounds to exactly 1.0 for a > 19.07, i.e. the profile of a sphere further away than
+	// R + 19.5/s is exactly 0 and cannot raise gl >= 0: skip its sqrt/tanh (result-neutral, bit for bit)
+	const double cut = radius + 19.5 / s;
+	const double cut2 = cut * cut;
 	for (int q0 = 0; q0 < count; q0 += chunk) {
 		int q = q0 + threadIdx.x;
 		__syncthreads();
@@ -683,7 +686,9 @@ __global__ void rasterise_kernel(double *gl, const double *bx, const double *by,
 		int m = min(chunk, count - q0);
 		for (int qq = 0; qq < m; ++qq) {
 			double dx = x - sb[qq], dy = y - sb[chunk + qq], dz = z - sb[2 * chunk + qq];
-			double d = sqrt(dx * dx + dy * dy + dz * dz) + 1E-10;
+			double d2 = dx * dx + dy * dy + dz * dz;
+			if (d2 > cut2) continue;
+			double d = sqrt(d2) + 1E-10;
 			double f = 0.5 * (1.0 - tanh(s * (d - radius)));
 			v = (v < f) ? f : v;
 		}
