@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--workload", default="400-SigmaP1-P-smallsigma")
     ap.add_argument("--attempts", type=int, default=30)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--zsweep", action="store_true", help="sweep z-chunk counts for a few tiles only")
     args = ap.parse_args()
     spec, _, _ = make_spec(args.workload, 1)
     # a developed state: IC + sphere pack, 40 attempts in
@@ -76,6 +77,14 @@ def main():
         for tx, ty in ((50, 3), (50, 2)):
             for zc in (4, 8, 16, 37, 74):
                 configs.append(({"PFT_TX": tx, "PFT_TY": ty, "PFT_ZCHUNKS": zc}, 0))
+    if args.zsweep:
+        configs = [({}, 0)]
+        for tx, ty in ((50, 5), (50, 3), (26, 5)):
+            if tx > spec.n1:
+                continue
+            for zc in (2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 25, 32, 40, 50):
+                if zc <= spec.n3:
+                    configs.append(({"PFT_TX": tx, "PFT_TY": ty, "PFT_ZCHUNKS": zc}, 0))
     for env, flags in configs:
         try:
             print(json.dumps(run(spec, fields, env, flags, args.attempts, t_h)), flush=True)
