@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("PFT_BENCH_WORKLOAD", "400-SigmaP1-P-smallsigma"))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="strict", choices=["strict", "fast"],
+                    help="strict = IEEE association, bit-exact (default); fast = FMA contraction allowed (fields within 1e-10, no step-sequence parity)")
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--profile-steps", type=int, default=40)
     args = ap.parse_args()
@@ -236,7 +238,9 @@ def main():
     N = world
 
     spec, scaling, geo = make_spec(args.workload, N)
-    sol = SlabSolver(spec, rank=rank, nranks=N, device=local)
+    from porousfreezethaw_b200 import _lib as _pftlib
+    lib_path = _pftlib.FAST_LIB_PATH if args.variant == "fast" else None
+    sol = SlabSolver(spec, rank=rank, nranks=N, device=local, lib_path=lib_path)
     if N > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -296,7 +300,7 @@ def main():
     os.environ["PFT_PROFILE_STAGES"] = "1"
     # (a second solver object: the profiling switch is read when a solver is created)
     u_, p_, gl_ = sol.download_interior()
-    solp = SlabSolver(spec, rank=rank, nranks=N, device=local)
+    solp = SlabSolver(spec, rank=rank, nranks=N, device=local, lib_path=lib_path)
     if N > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -374,7 +378,7 @@ def main():
             "steps": attempts, "warmup": args.warmup, "ms_per_step": dev_ms / max(attempts, 1),
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": spec.name, "grid": [spec.n1, spec.n2, spec.n3], "calc_mode": spec.calc_mode,
-                       "geometry": geo, "mode": "adaptive (delta 1e-3)", "cache": "inputs larger than L2 (no flush needed)"
+                       "geometry": geo, "mode": "adaptive (delta 1e-3)", "variant": args.variant, "cache": "inputs larger than L2 (no flush needed)"
                        if sol.cells * 13 * 8 > 2 * 126e6 else "working set fits L2",
                        "parallelism": f"z-slabs x{N}", "tile": [st["tile_x"], st["tile_y"]], "z_chunk": st["z_chunk"],
                        "rhs_evals_per_attempt": rhs / max(attempts, 1),

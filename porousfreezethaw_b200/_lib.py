@@ -10,6 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libpft_b200.so")
 RK_LIB_PATH = os.path.join(HERE, "csrc", "librk_b200.so")
+FAST_LIB_PATH = os.path.join(HERE, "csrc", "libpft_b200_fast.so")      # opt-in FMA variant (not bit-exact)
 
 NPARAM = 30
 _dp = C.POINTER(C.c_double)

@@ -66,7 +66,11 @@ static int fail(int code, const char *fmt, ...)
 	} while (0)
 
 extern "C" const char *pft_last_error(void) { return g_err; }
+#ifdef PFT_FAST_FP
+extern "C" const char *pft_version(void) { return "pft-b200 0.1 (sm_100a, float64, FAST variant: FMA contraction allowed, not bit-exact)"; }
+#else
 extern "C" const char *pft_version(void) { return "pft-b200 0.1 (sm_100a, float64, strict IEEE association)"; }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // NCCL through dlopen: single-GPU use must not require the library

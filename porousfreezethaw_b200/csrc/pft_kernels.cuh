@@ -30,8 +30,8 @@
 // come from a double-buffered shared-memory tile with a one-cell halo ring.
 #pragma once
 
-#ifndef PFT_STRICT_FP
-#error "pft_kernels.cuh must be compiled with -fmad=false -DPFT_STRICT_FP (strict IEEE association)"
+#if !defined(PFT_STRICT_FP) && !defined(PFT_FAST_FP)
+#error "pft_kernels.cuh must be compiled with -fmad=false -DPFT_STRICT_FP (strict IEEE association); -DPFT_FAST_FP builds the opt-in FMA variant"
 #endif
 
 #include <cuda_runtime.h>
