@@ -58,6 +58,11 @@ def make_spec(name: str, nranks: int):
         spec.initial_fields = lambda first_row=0, n3_local=None, _f=(u, p, gl), _s=spec: tuple(
             a[first_row:first_row + (_s.n3 if n3_local is None else n3_local)] for a in _f)
         return spec, "strong", f"case file {name[7:]}"
+    if name.startswith("slab-"):
+        # slab-200x50: one thin 200x200x50 block, calc_mode 1 (what one of 8 ranks owns of the 400 case)
+        n, nz = (int(v) for v in name[5:].split("x"))
+        spec = cases.cube_case(n, nz=nz, calc_mode=1, spheres=200)
+        return spec, "strong", "synthetic sphere pack (numpy default_rng(20251018), 200 spheres)"
     if name.startswith("cube-"):
         # cube-400 | cube-800 (strong scaling) | cube-800w (weak: 800x800x(100*N))
         tag = name[5:]
@@ -240,6 +245,8 @@ def main():
     spec, scaling, geo = make_spec(args.workload, N)
     from porousfreezethaw_b200 import _lib as _pftlib
     lib_path = _pftlib.FAST_LIB_PATH if args.variant == "fast" else None
+    if os.environ.get("PFT_BENCH_LIB"):       # A/B builds (development)
+        lib_path = os.environ["PFT_BENCH_LIB"]
     sol = SlabSolver(spec, rank=rank, nranks=N, device=local, lib_path=lib_path)
     if N > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -295,6 +302,14 @@ def main():
     value = total_cells * rhs / (dev_ms * 1e-3) / 1e6
     launches = st1["kernel_launches"] - st0["kernel_launches"]
     stage_launches = [a - b for a, b in zip(st1["stage_launches"], st0["stage_launches"])]
+    # host side of the control loop, per attempt: time blocked on the device's decision / time issuing launches
+    host_wait = (st1["host_wait_ms"] - st0["host_wait_ms"]) / max(attempts, 1)
+    host_launch = (st1["host_launch_ms"] - st0["host_launch_ms"]) / max(attempts, 1)
+    if N > 1:
+        hw = [None] * N
+        dist.all_gather_object(hw, (round(host_wait, 4), round(host_launch, 4), round(st1["device_ms_total"] / max(attempts, 1), 4)))
+    else:
+        hw = [(round(host_wait, 4), round(host_launch, 4), round(st1["device_ms_total"] / max(attempts, 1), 4))]
 
     # ---- per-stage device times (CUDA events around every stage kernel on its stream) ----
     os.environ["PFT_PROFILE_STAGES"] = "1"
@@ -385,6 +400,7 @@ def main():
                        "accepted": st1["accepted"] - st0["accepted"]},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "wall_ms_per_step": 1e3 * t_wall / max(attempts, 1),
+            "host_loop_ms_per_step": {"per_rank[wait, launch, device]": hw},
             "roofline_step": {"achieved": total_cells / N * sum(b * n for b, n in zip(sb, stage_launches)) / (dev_ms * 1e-3) / 1e9,
                               "peak": peak, "unit": "GB/s",
                               "frac": total_cells / N * sum(b * n for b, n in zip(sb, stage_launches)) / (dev_ms * 1e-3) / 1e9 / peak,

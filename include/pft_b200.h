@@ -105,6 +105,8 @@ typedef struct {
 	long   stage_launches[5];
 	int    tile_x, tile_y, z_chunk, threads, grid_blocks;
 	long   bytes_per_field;  /* device bytes of one field array incl. ghost planes */
+	double host_wait_ms;     /* host time spent waiting for the device's step decision */
+	double host_launch_ms;   /* host time spent issuing launches */
 } pft_stats;
 
 const char *pft_last_error(void);
@@ -143,6 +145,12 @@ int pft_reset_stats(pft_solver *s);
 /* debug/test hook: copy an internal array pair (u,p components) to compact host arrays.
  * which: 0 x, 1 K1, 2 aux3 (stage-3 input), 3 K3, 4 K4, 5 x_new (last attempt's candidate) */
 int pft_debug_fetch(pft_solver *s, int which, double *u, double *p);
+/* development builds only (-DPFT_TRACE, libpft_b200_trace.so): device timeline of the stage launches since
+ * the last call, 16 uint64 per launch (layout: csrc/pft_kernels.cuh); returns the record count */
+int pft_debug_trace(pft_solver *s, unsigned long long *records, int *stages, int max_records);
+/* same builds: per-CTA (start, end of body, end, smid<<32|chunk) of the first 12 launches since the last
+ * pft_debug_trace call, 1024 CTAs x 4 uint64 per launch; returns the number of launches copied */
+int pft_debug_trace_cta(pft_solver *s, unsigned long long *out, int launches);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <new>
@@ -182,7 +183,6 @@ struct pft_solver {
 	int peer_n3[PFT_MAX_RANKS];
 	unsigned int *halo_tickets;
 	unsigned long long hseq;                   // stage-launch sequence number (identical on all ranks)
-	StageArgs s5_args;                         // argument block of the last stage-5 launch (for eps_allreduce_kernel)
 	// TMA path (heat modes): one tensor map per array, box = tile + halo ring
 	bool use_tma;
 	bool split;           // split-phase mbarriers instead of a CTA barrier per plane
@@ -191,7 +191,13 @@ struct pft_solver {
 	CUtensorMap tmap_gl;
 	int bx, by, as;
 	size_t smem_tma[5];
+	// development build (-DPFT_TRACE): device timeline records, 16 x u64 per stage launch
+	unsigned long long *trace, *trace_cta;
+	std::vector<int> trace_stage;
 };
+#ifdef PFT_TRACE
+constexpr int TRACE_CAP = 4096, TRACE_REC = 16, TRACE_CTA_LAUNCHES = 12;
+#endif
 
 static double dirichlet(const pft_solver *s, double t)
 {
@@ -411,6 +417,11 @@ static void fill_peer_args(pft_solver *s, PeerArgs *pr, int out)
 		pr->hi_u = s->heat ? (double *)(pb + s->off[out][0]) : nullptr;
 		pr->hi_flag = &((SyncBlock *)pb)->halo_flag[0];
 	}
+#ifdef PFT_TRACE
+	// timing experiment only (wrong results): keep the flags, drop the plane pushes
+	static const int nopush = env_int("PFT_DEBUG_NOPUSH", 0);
+	if (nopush) pr->lo_p = pr->lo_u = pr->hi_p = pr->hi_u = nullptr;
+#endif
 }
 
 // stage launcher: fills the argument block for one Merson stage and (multi-GPU) exchanges the
@@ -442,7 +453,19 @@ static int launch_stage(pft_solver *s, int stage, double t_stage, double ha, dou
 		a.ctl = s->ctl; a.slot = s->slot_dev; a.seq = ++s->seq;
 		a.nblocks = s->grid.x * s->grid.y * s->grid.z;
 	}
-	if (stage == 5) s->s5_args = a;
+#ifdef PFT_TRACE
+	if (!s->trace) {
+		if (cudaMalloc(&s->trace, sizeof(unsigned long long) * TRACE_CAP * TRACE_REC) != cudaSuccess) return fail(PFT_ENOMEM, "trace buffer");
+		cudaMemsetAsync(s->trace, 0, sizeof(unsigned long long) * TRACE_CAP * TRACE_REC, s->stream);
+	}
+	if (!s->trace_cta) {
+		if (cudaMalloc(&s->trace_cta, sizeof(unsigned long long) * TRACE_CTA_LAUNCHES * 4096) != cudaSuccess) return fail(PFT_ENOMEM, "trace buffer");
+		cudaMemsetAsync(s->trace_cta, 0, sizeof(unsigned long long) * TRACE_CTA_LAUNCHES * 4096, s->stream);
+	}
+	a.trace = ((int)s->trace_stage.size() < TRACE_CAP) ? s->trace + s->trace_stage.size() * TRACE_REC : nullptr;
+	a.trace_cta = ((int)s->trace_stage.size() < TRACE_CTA_LAUNCHES) ? s->trace_cta + s->trace_stage.size() * 4096 : nullptr;
+	if (a.trace) s->trace_stage.push_back(stage);
+#endif
 	StageTimer tm{};
 	if (s->profile) {
 		cudaEventCreate(&tm.a); cudaEventCreate(&tm.b); tm.stage = stage;
@@ -778,6 +801,8 @@ extern "C" int pft_destroy(pft_solver *s)
 		if (s->peer_base[r] && s->peer_base[r] != s->slab) cudaIpcCloseMemHandle(s->peer_base[r]);
 	if (s->slab) cudaFree(s->slab);
 	if (s->halo_tickets) cudaFree(s->halo_tickets);
+	if (s->trace) cudaFree(s->trace);
+	if (s->trace_cta) cudaFree(s->trace_cta);
 	if (s->stage_buf) cudaFree(s->stage_buf);
 	if (s->ctl) cudaFree(s->ctl);
 	if (s->red) cudaFree(s->red);
@@ -917,6 +942,41 @@ extern "C" int pft_debug_fetch(pft_solver *s, int which, double *u, double *p)
 	return 0;
 }
 
+extern "C" int pft_debug_trace(pft_solver *s, unsigned long long *records, int *stages, int max_records)
+{
+	if (!s || !records || !stages) return fail(PFT_EINVAL, "null argument");
+#ifdef PFT_TRACE
+	CU(cudaSetDevice(s->device));
+	CU(cudaStreamSynchronize(s->stream));
+	const int n = std::min((int)s->trace_stage.size(), max_records);
+	if (n > 0) CU(cudaMemcpy(records, s->trace, sizeof(unsigned long long) * TRACE_REC * n, cudaMemcpyDeviceToHost));
+	for (int q = 0; q < n; q++) stages[q] = s->trace_stage[q];
+	s->trace_stage.clear();
+	if (s->trace) CU(cudaMemset(s->trace, 0, sizeof(unsigned long long) * TRACE_CAP * TRACE_REC));
+	return n;
+#else
+	(void)max_records;
+	return fail(PFT_EINVAL, "this library was built without -DPFT_TRACE (make libpft_b200_trace.so)");
+#endif
+}
+
+extern "C" int pft_debug_trace_cta(pft_solver *s, unsigned long long *out, int launches)
+{
+	if (!s || !out) return fail(PFT_EINVAL, "null argument");
+#ifdef PFT_TRACE
+	CU(cudaSetDevice(s->device));
+	CU(cudaStreamSynchronize(s->stream));
+	const int n = std::min(launches, TRACE_CTA_LAUNCHES);
+	if (!s->trace_cta) return 0;
+	CU(cudaMemcpy(out, s->trace_cta, sizeof(unsigned long long) * 4096 * n, cudaMemcpyDeviceToHost));
+	CU(cudaMemset(s->trace_cta, 0, sizeof(unsigned long long) * TRACE_CTA_LAUNCHES * 4096));
+	return n;
+#else
+	(void)launches;
+	return fail(PFT_EINVAL, "this library was built without -DPFT_TRACE (make libpft_b200_trace.so)");
+#endif
+}
+
 extern "C" int pft_rasterise(pft_solver *s, const double *xyz_raw, int count)
 {
 	if (!s || (count > 0 && !xyz_raw) || count < 0) return fail(PFT_EINVAL, "bad sphere list");
@@ -1011,6 +1071,13 @@ extern "C" int pft_rhs_host(pft_solver *s, double t, const double *w, double *dw
 #define CMD_NEXTFINISH  16
 #define CMD_BREAK       32
 
+static inline double host_ms()
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static int wait_slot(pft_solver *s, unsigned long long seq)
 {
 	volatile unsigned long long *p = &s->slot->seq;
@@ -1041,6 +1108,7 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 	int xc = A_X, xn = A_XN;              // current / candidate state pair (swapped on accept)
 	const bool multi = s->cs.nranks > 1;
 	int rc = 0, ret = PFT_SOLVE_DONE;
+	double t_host = 0.0;
 
 	sys->last_nan = 0;                    // :316
 	memset(s->st.stage_ms, 0, sizeof s->st.stage_ms);
@@ -1050,6 +1118,7 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 	if (h == 0 || fabs(final_time - t) <= fabs(h)) { h = final_time - t; command |= CMD_FINISHED; }
 
 	cudaEventRecord(s->ev0, s->stream);
+	t_host = host_ms();
 
 	if (!(s->k1_valid && s->k1_t == t) || (s->flags & PFT_FLAG_RECOMPUTE_K1)) {
 		if ((rc = launch_stage(s, 1, t, 0.0, 0.0, xc, A_K1, nullptr, sys, 0.0, 1.0))) goto device_error;   // :373
@@ -1070,13 +1139,15 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 
 		double eps; int nonfinite;
 		if (!multi || s->p2p) {
-			if (s->p2p) {      // device-side global max + decision: the role of MPI_Allreduce(MAX), :572
-				PFT_LAUNCH(eps_allreduce_kernel, dim3(1), dim3(32), 0, s->stream, s->s5_args, (SyncBlock *)s->slab);
-				s->st.kernel_launches++;
-			}
+			// (peer path: stage 5's last CTA has formed the global max + decision on the device, the role of
+			// MPI_Allreduce(MAX), :572)
 			if (s->speculate)          // K1 of the next step, gated on the device-side accept flag
 				if ((rc = launch_stage(s, 1, t + h, 0.0, 0.0, xn, A_K1, &s->ctl->accept, sys, 0.0, 1.0))) goto device_error;
+			const double tw = host_ms();
+			s->st.host_launch_ms += tw - t_host;
 			if ((rc = wait_slot(s, seq))) goto device_error;
+			t_host = host_ms();
+			s->st.host_wait_ms += t_host - tw;
 			eps = s->slot->eps; nonfinite = s->slot->nonfinite;
 		} else {
 			// NCCL path (PFT_COMM=nccl, or no peer access): global max over the slabs through the host

@@ -127,6 +127,10 @@ struct StageArgs {
 	unsigned int nblocks;
 	// stage 1 only: run only if *cond != 0 (speculative launch before the host's decision)
 	const int *cond;
+#ifdef PFT_TRACE
+	unsigned long long *trace;                  // development build: one timeline record per launch
+	unsigned long long *trace_cta;              // and (start, end of body, end, smid<<32|chunk) per CTA of the first launches
+#endif
 };
 
 struct KParams {
@@ -153,10 +157,13 @@ __device__ __forceinline__ double face_flux(const Consts &c, double pa, double p
 }
 
 // a / b for b > 0.  A zero numerator (exact in the bulk of the domain: uniform temperature, p == 0
-// or 1) sends nvcc's IEEE division through its out-of-range slow path (a ~60-instruction
+// or 1) sends nvcc's IEEE division through its out-of-range slow path (a ~70-instruction
 // subroutine, measured at a third of all executed instructions).  (+-0)/b == +-0 for positive b,
 // so divide a harmless 1.0 instead and select the zero afterwards: every lane stays on the
 // correctly-rounded fast path, non-zero operands are untouched.
+// (Numerators below ~2^-960 -- the far tail of the phase field, 1e-290 ... 1e-323 -- still take the
+// subroutine.  An exact rescaling of those was built and verified bit for bit, and rejected: its
+// extra branches cost 3 % on every division, more than the tail costs; profiles/round1_tuning.md.)
 __device__ __forceinline__ double div_pos(double a, double b)
 {
 	const bool z = (a == 0.0);
@@ -256,8 +263,25 @@ __device__ __forceinline__ int chunk_of_block(int nzc)
 {
 	const int z = blockIdx.z;
 	if (nzc < 3) return z;
-	return z == 0 ? 0 : (z == 1 ? nzc - 1 : z - 1);
+	return z == 0 ? nzc - 1 : (z == 1 ? 0 : z - 1);      // the top chunk pushes its plane last: give it the head start
 }
+
+// ---- development build (-DPFT_TRACE): per-launch timeline from %globaltimer -----------------------
+// record: [0] ~first CTA start  [1] last CTA start  [2] last CTA end  [3] last lower-boundary CTA past
+// its wait  [4] same, upper  [5] longest wait (ns)  [6] lower flag published  [7] upper flag published
+// [8] stage 5: error-max exchange starts  [9] decision published  [10] longest halo_signal (ns)
+// [11..13] longest CTA body (ns) among lower-boundary / upper-boundary / interior chunks
+#ifdef PFT_TRACE
+__device__ __forceinline__ unsigned long long gtime()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+#define PFT_TRACE_MAX(a, i, v) do { if ((a).trace) atomicMax(&(a).trace[i], (unsigned long long)(v)); } while (0)
+#else
+#define PFT_TRACE_MAX(a, i, v) do { } while (0)
+#endif
 
 __device__ __forceinline__ void halo_wait(const PeerArgs &pr, bool lo, bool hi, int tid)
 {
@@ -274,9 +298,13 @@ __device__ __forceinline__ void halo_signal(const PeerArgs &pr, bool lo, bool hi
 {
 	const bool wl = lo && pr.wait_lo, wh = hi && pr.wait_hi;
 	if (!(wl || wh)) return;
-	__threadfence_system();              // this thread's peer stores are visible system-wide ...
-	__syncthreads();                     // ... for every thread of the CTA, before it is counted
+	__syncthreads();                     // every thread's peer stores happen before thread 0's ticket (CTA barrier) ...
 	if (tid == 0) {
+		// ... a device-scope release per CTA, and ONE system-scope fence per side and launch, by the CTA that
+		// takes the last ticket: causality is transitive (barrier -> device-scope release/acquire on the ticket
+		// -> system-scope release of the flag).  A system fence in every boundary CTA queued up for 5-10 us
+		// when the boundary CTAs of a launch finish together (measured, profiles/round1_tuning.md).
+		__threadfence();
 		const unsigned int n = gridDim.x * gridDim.y;
 		if (wl && atomicAdd(&pr.tickets[0], 1u) == n - 1) { pr.tickets[0] = 0u; __threadfence_system(); st_release_sys(pr.lo_flag, pr.hseq); }
 		if (wh && atomicAdd(&pr.tickets[1], 1u) == n - 1) { pr.tickets[1] = 0u; __threadfence_system(); st_release_sys(pr.hi_flag, pr.hseq); }
@@ -302,13 +330,18 @@ __device__ __forceinline__ void store_out(const StageArgs &a, long long o, long 
 	if (k == n3 - 1 && a.pr.hi_p) { a.pr.hi_p[col] = vp; if (HEAT) a.pr.hi_u[col] = vu; }
 }
 
-// ---- stage 5 epilogue: grid-wide max of the error estimate, acceptance decision, host notification
+// ---- stage 5 epilogue: grid-wide max of the error estimate, acceptance decision, host notification.
+// Several GPUs: the last CTA of every rank's launch hands its slab maximum to every rank (peer stores,
+// one thread per rank), waits for the others' and forms the global maximum -- the role of
+// MPI_Allreduce(MAX), RK_MPI_SAsolver_hybrid2.c:572 -- so that every rank takes the same decision
+// without a further launch.  Peers never wait for THIS CTA (their boundary waits concern CTAs that
+// are long finished), so the spin cannot deadlock.
 __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, double emax, int nonfinite)
 {
 	// CTA max through a shared-memory atomic on the bit pattern (non-negative doubles order
 	// like their uint64 patterns; the tile need not be a multiple of the warp size)
 	__shared__ unsigned long long s_bits;
-	__shared__ int s_nonfinite;
+	__shared__ int s_nonfinite, s_last;
 	if (tid == 0) { s_bits = 0ull; s_nonfinite = 0; }
 	__syncthreads();
 	if (emax > 0.0) atomicMax(&s_bits, (unsigned long long)__double_as_longlong(emax));
@@ -319,41 +352,60 @@ __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, doubl
 		if (s_bits) atomicMax(&ctl->eps_bits, s_bits);
 		if (s_nonfinite) atomicOr(&ctl->nonfinite, 1);
 		__threadfence();
-		unsigned int t = atomicAdd(&ctl->ticket, 1u);
-		if (t == a.nblocks - 1) {            // last CTA of the launch: every other CTA's max is in
+		const unsigned int t = atomicAdd(&ctl->ticket, 1u);
+		s_last = (t == a.nblocks - 1);
+		if (s_last) {                        // last CTA of the launch: every other CTA's max is in
 			__threadfence();
-			unsigned long long bits = atomicMax(&ctl->eps_bits, 0ull);
-			int nfl = atomicOr(&ctl->nonfinite, 0);
-			double eps = __longlong_as_double((long long)bits);
-			double ecmp = a.scale_eps ? eps * a.eps_scale : eps;            // RK_MPI_SAsolver_hybrid2.c:578
-			int acc = (ecmp < a.delta) || (a.h_abs < a.h_min);               // :599
-			if (a.handle_nan && nfl) acc = 0;                                 // :626-646
+			s_bits = atomicMax(&ctl->eps_bits, 0ull);
+			s_nonfinite = atomicOr(&ctl->nonfinite, 0);
 			ctl->eps_bits = 0ull;
 			ctl->nonfinite = 0;
 			ctl->ticket = 0u;
-			if (a.pr.nranks > 1) {
-				// peer path: hand this slab's maximum to every rank; eps_allreduce_kernel (next in
-				// every rank's stream) forms the global maximum and the decision
-				const int b = (int)(a.seq & 1ull);
-				for (int r = 0; r < a.pr.nranks; r++) {
-					EpsSlot *e = &a.pr.ranks[r]->slot[b][a.pr.rank];
-					e->eps = eps;
-					e->nonfinite = nfl;
-				}
-				__threadfence_system();
-				for (int r = 0; r < a.pr.nranks; r++) st_release_sys(&a.pr.ranks[r]->slot[b][a.pr.rank].seq, a.seq);
-				return;
-			}
-			ctl->accept = acc;
-			__threadfence();
-			HostSlot *s = a.slot;
-			s->eps = eps;
-			s->accept = acc;
-			s->nonfinite = nfl;
-			__threadfence_system();
-			*(volatile unsigned long long *)&s->seq = a.seq;
-			__threadfence_system();
 		}
+	}
+	__syncthreads();
+	if (!s_last) return;                     // CTA-uniform
+
+	if (a.pr.nranks > 1) {
+		const int b = (int)(a.seq & 1ull);
+		const int nthr = blockDim.x * blockDim.y;
+		if (tid == 0) PFT_TRACE_MAX(a, 8, gtime());
+		const double mine = __longlong_as_double((long long)s_bits);
+		const int mine_nf = s_nonfinite;
+		__syncthreads();                     // everyone has read the slab result before it is overwritten below
+		for (int r = tid; r < a.pr.nranks; r += nthr) {
+			EpsSlot *e = &a.pr.ranks[r]->slot[b][a.pr.rank];
+			e->eps = mine;
+			e->nonfinite = mine_nf;
+			__threadfence_system();
+			st_release_sys(&e->seq, a.seq);
+		}
+		if (tid == 0) { s_bits = 0ull; s_nonfinite = 0; }
+		__syncthreads();
+		for (int r = tid; r < a.pr.nranks; r += nthr) {
+			const EpsSlot *e = &a.pr.ranks[a.pr.rank]->slot[b][r];
+			while (ld_acquire_sys(&e->seq) != a.seq) { }
+			const double v = *(volatile const double *)&e->eps;
+			if (v > 0.0) atomicMax(&s_bits, (unsigned long long)__double_as_longlong(v));
+			if (*(volatile const int *)&e->nonfinite) atomicOr(&s_nonfinite, 1);
+		}
+		__syncthreads();
+	}
+	if (tid == 0) {
+		const double eps = __longlong_as_double((long long)s_bits);
+		const int nfl = s_nonfinite;
+		const double ecmp = a.scale_eps ? eps * a.eps_scale : eps;        // RK_MPI_SAsolver_hybrid2.c:578
+		int acc = (ecmp < a.delta) || (a.h_abs < a.h_min);                 // :599
+		if (a.handle_nan && nfl) acc = 0;                                   // :626-646
+		a.ctl->accept = acc;
+		__threadfence();
+		HostSlot *s = a.slot;
+		s->eps = eps;
+		s->accept = acc;
+		s->nonfinite = nfl;
+		__threadfence_system();
+		*(volatile unsigned long long *)&s->seq = a.seq;
+		PFT_TRACE_MAX(a, 9, gtime());
 	}
 }
 
@@ -580,44 +632,6 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 
 	halo_signal(a.pr, chunk_lo, chunk_hi, tid);
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
-}
-
-// global maximum of the per-slab error estimates + the acceptance decision (peer path): one
-// warp, lane r waits for rank r's slot of this attempt.  Plays the role of MPI_Allreduce(MAX)
-// (RK_MPI_SAsolver_hybrid2.c:572) without leaving the device.
-__global__ void eps_allreduce_kernel(StageArgs a, SyncBlock *mine)
-{
-	const int r = threadIdx.x;
-	const int b = (int)(a.seq & 1ull);
-	double eps = 0.0;
-	int nf = 0;
-	if (r < a.pr.nranks) {
-		const EpsSlot *e = &mine->slot[b][r];
-		while (ld_acquire_sys(&e->seq) != a.seq) { }
-		eps = *(volatile const double *)&e->eps;
-		nf = *(volatile const int *)&e->nonfinite;
-	}
-#ifndef PFT_CUDA_EMU
-	for (int o = 16; o > 0; o >>= 1) {
-		double w = __shfl_xor_sync(0xffffffffu, eps, o);
-		eps = (w > eps) ? w : eps;
-		nf |= __shfl_xor_sync(0xffffffffu, nf, o);
-	}
-#endif
-	if (r == 0) {
-		double ecmp = a.scale_eps ? eps * a.eps_scale : eps;            // RK_MPI_SAsolver_hybrid2.c:578
-		int acc = (ecmp < a.delta) || (a.h_abs < a.h_min);               // :599
-		if (a.handle_nan && nf) acc = 0;                                  // :626-646
-		a.ctl->accept = acc;
-		__threadfence();
-		HostSlot *s = a.slot;
-		s->eps = eps;
-		s->accept = acc;
-		s->nonfinite = nf;
-		__threadfence_system();
-		*(volatile unsigned long long *)&s->seq = a.seq;
-		__threadfence_system();
-	}
 }
 
 // ----------------------------------------------------------------------------------------

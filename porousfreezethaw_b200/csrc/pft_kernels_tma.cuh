@@ -255,7 +255,19 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 		fence_mbar_init();
 	}
 	__syncthreads();
+#ifdef PFT_TRACE
+	unsigned long long tr_t0 = 0;
+	if (tid == 0) { tr_t0 = gtime(); PFT_TRACE_MAX(a, 0, ~tr_t0); PFT_TRACE_MAX(a, 1, tr_t0); }
+#endif
 	halo_wait(a.pr, chunk_lo, chunk_hi, tid);     // peer path: the neighbours' planes of the previous launch have landed
+#ifdef PFT_TRACE
+	if (tid == 0 && (chunk_lo || chunk_hi)) {
+		const unsigned long long t1 = gtime();
+		if (chunk_lo) PFT_TRACE_MAX(a, 3, t1);
+		if (chunk_hi) PFT_TRACE_MAX(a, 4, t1);
+		PFT_TRACE_MAX(a, 5, t1 - tr_t0);
+	}
+#endif
 
 	// thread 0 requests plane q into raw buffer b: one tensor copy per array
 	const uint32_t plane_bytes = (uint32_t)(NA * BX * P.by * sizeof(double));
@@ -394,7 +406,30 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 		if (FORM) { tc = tn; tn = (tn + 1 == NT) ? 0 : tn + 1; }
 	}
 
+#ifdef PFT_TRACE
+	unsigned long long tr_t1 = 0;
+	if (tid == 0) tr_t1 = gtime();
+#endif
 	halo_signal(a.pr, chunk_lo, chunk_hi, tid);
+#ifdef PFT_TRACE
+	if (tid == 0) {
+		const unsigned long long t2 = gtime();
+		if ((chunk_lo && a.pr.wait_lo) || (chunk_hi && a.pr.wait_hi)) PFT_TRACE_MAX(a, 10, t2 - tr_t1);   // longest halo_signal
+		PFT_TRACE_MAX(a, chunk_lo ? 11 : (chunk_hi ? 12 : 13), tr_t1 - tr_t0);                            // longest CTA body per chunk class
+		PFT_TRACE_MAX(a, 2, t2);
+		if (a.trace_cta) {
+			const unsigned int lb = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+			if (lb < 1024u) {
+				unsigned int smid;
+				asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+				unsigned long long *r = a.trace_cta + 4ull * lb;
+				r[0] = tr_t0; r[1] = tr_t1; r[2] = t2; r[3] = ((unsigned long long)smid << 32) | (unsigned int)(k0 / g.zc);
+			}
+		}
+		if (chunk_lo) PFT_TRACE_MAX(a, 6, t2);      // the last one to pass here is (about) when the flag went out
+		if (chunk_hi) PFT_TRACE_MAX(a, 7, t2);
+	}
+#endif
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
 }
 

@@ -132,6 +132,23 @@ class SlabSolver:
         self._check(self.lib.pft_debug_fetch(self._h, which, _ptr(u), _ptr(p)), "pft_debug_fetch")
         return u, p
 
+    def debug_trace(self, max_records: int = 4096):
+        """development builds (libpft_b200_trace.so): (stages, records[n][16]) of the launches since the last call"""
+        rec = np.zeros((max_records, 16), dtype=np.uint64)
+        stg = np.zeros(max_records, dtype=np.int32)
+        n = self.lib.pft_debug_trace(self._h, rec.ctypes.data_as(C.POINTER(C.c_ulonglong)), stg.ctypes.data_as(C.POINTER(C.c_int)), max_records)
+        if n < 0:
+            raise PftError(f"pft_debug_trace failed ({n}): {self.lib.pft_last_error().decode()}")
+        return stg[:n].copy(), rec[:n].copy()
+
+    def debug_trace_cta(self, launches: int = 12):
+        """development builds: per-CTA records [launch][1024][4] (start, end of body, end, smid<<32|chunk)"""
+        out = np.zeros((launches, 1024, 4), dtype=np.uint64)
+        n = self.lib.pft_debug_trace_cta(self._h, out.ctypes.data_as(C.POINTER(C.c_ulonglong)), launches)
+        if n < 0:
+            raise PftError(f"pft_debug_trace_cta failed ({n}): {self.lib.pft_last_error().decode()}")
+        return out[:n]
+
     def rasterise(self, spheres_raw: np.ndarray):
         s = np.ascontiguousarray(spheres_raw, dtype=np.float64).reshape(-1, 3)
         self._check(self.lib.pft_rasterise(self._h, _ptr(s), s.shape[0]), "pft_rasterise")

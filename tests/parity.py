@@ -48,7 +48,19 @@ def assert_fields(case, got, want, exact: bool, what: str):
 def check_rhs(spec, lib_path, exact=True, t=0.0, flags=0, perturb=True):
     """K = f(t, w) through the RK_RightHandSide-shaped entry point (pft_rhs_host)."""
     case, orc, w = make(spec)
-    if perturb:   # a smooth non-trivial temperature / phase state so that every term is live
+    if perturb == "tiny":
+        # the far tail of the phase field ahead of an interface: |p| from 1e-200 down through the
+        # subnormals to exact zeros, both signs, under a (mostly) uniform temperature -- tiny and
+        # subnormal numerators and quotients in every division of the right-hand side
+        rng = np.random.default_rng(12)
+        W = w.reshape(3, case.N3, case.N2, case.N1)
+        shape = (case.n3, case.n2, case.n1)
+        mag = 10.0 ** rng.uniform(-332, -200, size=shape)          # < 4.9e-324 underflows to 0
+        W[1, 2:-2, 2:-2, 2:-2] = mag * rng.choice([-1.0, 1.0], size=shape)
+        W[0, 2:-2, 2:-2, 2:-2] = 272.0
+        W[0, 2:-2, 2:-2, 2:-2][rng.random(shape) < 0.02] += 1.0
+        assert np.count_nonzero((np.abs(W[1]) > 0) & (np.abs(W[1]) < 2.3e-308)) > 0
+    elif perturb:   # a smooth non-trivial temperature / phase state so that every term is live
         rng = np.random.default_rng(11)
         W = w.reshape(3, case.N3, case.N2, case.N1)
         W[0, 2:-2, 2:-2, 2:-2] += rng.uniform(-30, 5, size=(case.n3, case.n2, case.n1))

@@ -12,6 +12,11 @@ def test_rhs(emu_lib, mode):
     parity.check_rhs(cases.small_case(12, 10, 16, calc_mode=mode), emu_lib)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_rhs_tiny_and_subnormal_values(emu_lib, mode):
+    parity.check_rhs(cases.small_case(12, 10, 16, calc_mode=mode), emu_lib, perturb="tiny")
+
+
 @pytest.mark.parametrize("mode,flags", [(0, 0), (0, 16), (0, 8), (0, 24), (1, 0), (1, 16), (2, 0), (2, 16), (10, 0)])
 def test_fused_stages(emu_lib, mode, flags):
     parity.check_fused_stages(cases.small_case(12, 10, 8, calc_mode=mode), emu_lib, flags=flags)

@@ -33,6 +33,13 @@ def test_rhs_bit_exact(gpu_lib, mode):
     parity.check_rhs(cases.small_case(24, 20, 32, calc_mode=mode), gpu_lib)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 11])
+def test_rhs_tiny_and_subnormal_values_bit_exact(gpu_lib, mode):
+    """the far tail of the phase field (1e-200 ... subnormal ... 0): tiny and subnormal numerators and
+    quotients in every division of the right-hand side keep their bits (no flush-to-zero anywhere)"""
+    parity.check_rhs(cases.small_case(24, 20, 32, calc_mode=mode), gpu_lib, perturb="tiny")
+
+
 def test_rhs_mode2_tolerance(gpu_lib):
     parity.check_rhs(cases.small_case(24, 20, 32, calc_mode=2), gpu_lib, exact=False)
 

@@ -71,3 +71,4 @@ def test_solver_module_return_codes():
     rk.RK_MPI_SA_handle_NAN(5)
     assert rk.RK_MPI_SA_check_NAN() == 0
     assert rk.RK_MPI_SA_cleanup() == 0
+

@@ -79,10 +79,10 @@ def main():
                 configs.append(({"PFT_TX": tx, "PFT_TY": ty, "PFT_ZCHUNKS": zc}, 0))
     if args.zsweep:
         configs = [({}, 0)]
-        for tx, ty in ((50, 5), (50, 3), (26, 5)):
+        for tx, ty in ((50, 5), (50, 4), (50, 3), (100, 2), (40, 5)):
             if tx > spec.n1:
                 continue
-            for zc in (2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 25, 32, 40, 50):
+            for zc in (1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 25, 32, 40, 50):
                 if zc <= spec.n3:
                     configs.append(({"PFT_TX": tx, "PFT_TY": ty, "PFT_ZCHUNKS": zc}, 0))
     for env, flags in configs:
