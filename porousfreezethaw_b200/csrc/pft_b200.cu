@@ -42,8 +42,21 @@ using namespace pft;
 // test infrastructure: the product library is only ever built by nvcc for sm_100a.
 #ifdef PFT_CUDA_EMU
 #define PFT_LAUNCH(kernel, grid, block, smem, stream, ...) pft_emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+#define PFT_LAUNCH_PDL(pdl, kernel, grid, block, smem, stream, arg) PFT_LAUNCH(kernel, grid, block, smem, stream, arg)
 #else
 #define PFT_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// stage kernels: programmatic stream serialization -- the launch may begin while its predecessor in the
+// stream drains; the kernels order themselves with griddepcontrol (pdl_wait / pdl_launch, pft_kernels.cuh)
+#define PFT_LAUNCH_PDL(pdl_, kernel_, grid_, block_, smem_, stream_, arg_)                           \
+	do {                                                                                             \
+		cudaLaunchConfig_t cfg_ = {};                                                                \
+		cfg_.gridDim = (grid_); cfg_.blockDim = (block_); cfg_.dynamicSmemBytes = (smem_); cfg_.stream = (stream_); \
+		cudaLaunchAttribute at_[1];                                                                  \
+		at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                              \
+		at_[0].val.programmaticStreamSerializationAllowed = (pdl_) ? 1 : 0;                          \
+		cfg_.attrs = at_; cfg_.numAttrs = 1;                                                         \
+		cudaLaunchKernelEx(&cfg_, kernel_, arg_);                                                    \
+	} while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -171,6 +184,7 @@ struct pft_solver {
 	ncclComm_t comm;
 	bool have_comm;
 	bool profile;
+	bool pdl;             // stage kernels use programmatic dependent launch (off while profiling stages)
 	std::vector<StageTimer> timers;
 	pft_stats st;
 	// one device slab: [SyncBlock][13 field arrays]; peers map it with CUDA IPC
@@ -330,7 +344,7 @@ static cudaError_t launch_t(pft_solver *s, const KParams &kp)
 		if (e != cudaSuccess) return e;
 		attr_set = true;
 	}
-	PFT_LAUNCH(fn, s->grid, s->block, s->smem, s->stream, kp);
+	PFT_LAUNCH_PDL(s->pdl, fn, s->grid, s->block, s->smem, s->stream, kp);
 	return cudaGetLastError();
 }
 
@@ -356,7 +370,7 @@ static cudaError_t launch_tma_t(pft_solver *s, const TmaParams &kp)
 		if (e != cudaSuccess) return e;
 		attr_set = true;
 	}
-	PFT_LAUNCH(fn, s->grid, s->block, s->smem_tma[STAGE - 1], s->stream, kp);
+	PFT_LAUNCH_PDL(s->pdl, fn, s->grid, s->block, s->smem_tma[STAGE - 1], s->stream, kp);
 	return cudaGetLastError();
 }
 
@@ -370,7 +384,7 @@ static cudaError_t launch_tma2_t(pft_solver *s, const TmaParams &kp)
 		if (e != cudaSuccess) return e;
 		attr_set = true;
 	}
-	PFT_LAUNCH(fn, s->grid, s->block, s->smem_tma[STAGE - 1], s->stream, kp);
+	PFT_LAUNCH_PDL(s->pdl, fn, s->grid, s->block, s->smem_tma[STAGE - 1], s->stream, kp);
 	return cudaGetLastError();
 }
 
@@ -678,6 +692,7 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	s->speculate_req = !(flags & PFT_FLAG_NO_SPECULATION) && !env_int("PFT_NO_SPECULATION", 0);
 	s->speculate = s->speculate_req && cs->nranks == 1;      // N > 1: enabled by the peer path (setup_p2p)
 	s->profile = env_int("PFT_PROFILE_STAGES", 0) != 0;
+	s->pdl = !s->profile && env_int("PFT_NO_PDL", 0) == 0;
 	make_consts(s);
 
 	Geom &g = s->g;

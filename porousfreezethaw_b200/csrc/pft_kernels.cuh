@@ -257,6 +257,19 @@ inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return *
 inline void st_release_sys(unsigned long long *p, unsigned long long v) { *p = v; }
 #endif
 
+// programmatic dependent launch (stage kernels are launched with programmatic stream serialization):
+// pdl_launch() lets the NEXT launch of the stream start filling SMs as this launch's CTAs retire -- it
+// fires once every CTA of this launch has issued it, so the successor never competes with this launch
+// for SM slots; pdl_wait() blocks until the PREVIOUS launch has completed and its writes are visible.
+// What a CTA does before pdl_wait() (index arithmetic, barrier set-up) overlaps the predecessor's tail.
+#ifndef PFT_CUDA_EMU
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+inline void pdl_wait() {}
+inline void pdl_launch() {}
+#endif
+
 // chunk processed by this CTA: the two boundary chunks come first in launch order, so that
 // their planes reach the neighbours while the interior is still being computed
 __device__ __forceinline__ int chunk_of_block(int nzc)
@@ -419,6 +432,8 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 	const Geom &g = P.g;
 	const StageArgs &a = P.a;
 
+	pdl_launch();
+	pdl_wait();
 	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) { halo_skip(a.pr); return; } }
 
 	constexpr int NF = HEAT ? 3 : 1;        // fields kept in the shared tile: p [, u, gl]

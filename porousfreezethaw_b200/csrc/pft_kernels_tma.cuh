@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 	const Geom &g = P.g;
 	const StageArgs &a = P.a;
 
-	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) { halo_skip(a.pr); return; } }
+	pdl_launch();
 
 	constexpr int NP = stage_np(STAGE);
 	constexpr int NA = 2 * NP + 1;
@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 		fence_mbar_init();
 	}
 	__syncthreads();
+	pdl_wait();                                   // from here on this launch reads what its predecessor wrote
+	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) { halo_skip(a.pr); return; } }
 #ifdef PFT_TRACE
 	unsigned long long tr_t0 = 0;
 	if (tid == 0) { tr_t0 = gtime(); PFT_TRACE_MAX(a, 0, ~tr_t0); PFT_TRACE_MAX(a, 1, tr_t0); }
@@ -446,6 +448,8 @@ __global__ void __launch_bounds__(256, 2) merson_stage_tma2(const __grid_constan
 	const Geom &g = P.g;
 	const StageArgs &a = P.a;
 
+	pdl_launch();
+	pdl_wait();
 	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) { halo_skip(a.pr); return; } }
 
 	constexpr int NP = stage_np(STAGE);
