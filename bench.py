@@ -216,7 +216,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="strict", choices=["strict", "fast"],
                     help="strict = IEEE association, bit-exact (default); fast = FMA contraction allowed (fields within 1e-10, no step-sequence parity)")
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--fixed-step", action="store_true",
+                    help="SURVEY.md 8(d) fixed-step mode: H = half the adaptive step reached after the warm-up, h_min = inf, one solve call per step")
+    ap.add_argument("--cpu-steps", type=int, default=50)
     ap.add_argument("--profile-steps", type=int, default=40)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -285,17 +287,33 @@ def main():
 
     # ---- warm-up, then EXACTLY K attempts, device-resident --------------------------------
     sol.solve(T_END, max_attempts=args.warmup)
+    H = 0.5 * sol.sys.h                                      # fixed-step mode: identical on every rank
+
+    def advance(s, k):
+        """k step attempts; returns this rank's device time (CUDA events on the solver's stream)"""
+        if not args.fixed_step:
+            s.solve(T_END, max_attempts=k)
+            return s.stats()["device_ms_total"]
+        ms = 0.0
+        for _ in range(k):                                   # one always-accepted Merson step per call (SURVEY.md 8(d))
+            s.sys.h, s.sys.h_min = H, float("inf")
+            s.solve(s.sys.t + H)
+            ms += s.stats()["device_ms_total"]
+        return ms
+
+    if args.fixed_step:
+        advance(sol, 3)
     st0 = sol.stats()
     ev0 = sol.sys.rhs_evals
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     t_wall = time.perf_counter()
-    r = sol.solve(T_END, max_attempts=args.steps)
+    my_ms = advance(sol, args.steps)
     barrier()
     t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if sampler else None
     st1 = sol.stats()
-    dev_ms = allmax(st1["device_ms_total"])                 # CUDA events on the solver's own stream, max over ranks
+    dev_ms = allmax(my_ms)                                   # max over ranks
     attempts = st1["attempts"] - st0["attempts"]
     rhs = sol.sys.rhs_evals - ev0
     total_cells = allsum(float(sol.cells))
@@ -307,9 +325,9 @@ def main():
     host_launch = (st1["host_launch_ms"] - st0["host_launch_ms"]) / max(attempts, 1)
     if N > 1:
         hw = [None] * N
-        dist.all_gather_object(hw, (round(host_wait, 4), round(host_launch, 4), round(st1["device_ms_total"] / max(attempts, 1), 4)))
+        dist.all_gather_object(hw, (round(host_wait, 4), round(host_launch, 4), round(my_ms / max(attempts, 1), 4)))
     else:
-        hw = [(round(host_wait, 4), round(host_launch, 4), round(st1["device_ms_total"] / max(attempts, 1), 4))]
+        hw = [(round(host_wait, 4), round(host_launch, 4), round(my_ms / max(attempts, 1), 4))]
 
     # ---- per-stage device times (CUDA events around every stage kernel on its stream) ----
     os.environ["PFT_PROFILE_STAGES"] = "1"
@@ -325,10 +343,11 @@ def main():
     solp.upload_interior(u_, p_, gl_)
     solp.sys.t, solp.sys.h = sol.sys.t, sol.sys.h
     del u_, p_, gl_
-    solp.solve(T_END, max_attempts=3)
+    solp.sys.h_min = sol.sys.h_min
+    advance(solp, 3)
     solp.reset_stats()
     barrier()
-    solp.solve(T_END, max_attempts=args.profile_steps)
+    advance(solp, args.profile_steps)
     barrier()
     stp = solp.stats()
     del os.environ["PFT_PROFILE_STAGES"]
@@ -367,7 +386,7 @@ def main():
     a0 = sol.sys.steps_total
     t0 = time.perf_counter()
     sol.upload(xh)
-    sol.solve(T_END, max_attempts=args.steps)
+    advance(sol, args.steps)
     sol.download(xh)
     barrier()
     e2e_s = allmax(time.perf_counter() - t0)
@@ -393,7 +412,7 @@ def main():
             "steps": attempts, "warmup": args.warmup, "ms_per_step": dev_ms / max(attempts, 1),
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": spec.name, "grid": [spec.n1, spec.n2, spec.n3], "calc_mode": spec.calc_mode,
-                       "geometry": geo, "mode": "adaptive (delta 1e-3)", "variant": args.variant, "cache": "inputs larger than L2 (no flush needed)"
+                       "geometry": geo, "mode": f"fixed step H={H:.6g}" if args.fixed_step else "adaptive (delta 1e-3)", "variant": args.variant, "cache": "inputs larger than L2 (no flush needed)"
                        if sol.cells * 13 * 8 > 2 * 126e6 else "working set fits L2",
                        "parallelism": f"z-slabs x{N}", "tile": [st["tile_x"], st["tile_y"]], "z_chunk": st["z_chunk"],
                        "rhs_evals_per_attempt": rhs / max(attempts, 1),

@@ -100,8 +100,8 @@ typedef struct {
 	long   rhs_evals;
 	long   attempts, accepted;
 	double device_ms_total;  /* device time of the last pft_solve (CUDA events on the solver stream) */
-	double stage_ms[5];      /* device time per Merson stage kernel, summed over the last pft_solve
-	                            (only collected when PFT_PROFILE_STAGES=1) */
+	double stage_ms[5];      /* device time per Merson stage kernel, summed since pft_reset_stats like
+	                            stage_launches (only collected when PFT_PROFILE_STAGES=1) */
 	long   stage_launches[5];
 	int    tile_x, tile_y, z_chunk, threads, grid_blocks;
 	long   bytes_per_field;  /* device bytes of one field array incl. ghost planes */

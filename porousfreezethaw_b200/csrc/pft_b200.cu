@@ -1126,7 +1126,6 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 	double t_host = 0.0;
 
 	sys->last_nan = 0;                    // :316
-	memset(s->st.stage_ms, 0, sizeof s->st.stage_ms);
 
 	// :319-325
 	if ((final_time > t && h < 0) || (final_time < t && h > 0)) h *= -1;

@@ -5,4 +5,4 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; 
 timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "rc=$?" >> gpurun_out/bench_ref.err
 timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
-tail -3 gpurun_out/smoke.log gpurun_out/pytest_gpu.log gpurun_out/bench_ref.err gpurun_out/bench.err
+for f in smoke.log pytest_gpu.log bench_ref.err bench.err; do tail -n 3 gpurun_out/$f; done
