@@ -658,6 +658,16 @@ extern "C" int pft_comm_init(pft_solver *s, const void *id128)
 
 // ------------------------------------------------------------------------------------------
 
+// inside pft_create, once the solver object exists: release it on the way out of a failed CUDA call
+#define CUS(call)                                                                                    \
+	do {                                                                                             \
+		cudaError_t e_ = (call);                                                                     \
+		if (e_ != cudaSuccess) {                                                                     \
+			pft_destroy(s);                                                                          \
+			return fail(PFT_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+		}                                                                                            \
+	} while (0)
+
 extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_solver **out)
 {
 	if (!cs || !out) return fail(PFT_EINVAL, "null argument");
@@ -739,9 +749,9 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 		s->smem = (2 * NF * ts + fl) * sizeof(double);
 	}
 
-	CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-	CU(cudaEventCreate(&s->ev0)); CU(cudaEventCreate(&s->ev1));
-	CU(cudaEventCreateWithFlags(&s->ev_red, cudaEventDisableTiming));
+	CUS(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	CUS(cudaEventCreate(&s->ev0)); CU(cudaEventCreate(&s->ev1));
+	CUS(cudaEventCreateWithFlags(&s->ev_red, cudaEventDisableTiming));
 	const size_t fb = ((size_t)s->field * sizeof(double) + 255) & ~(size_t)255;
 	{
 		// layout: identical on every rank of a run with equal slab depth; offsets are exchanged anyway
@@ -757,14 +767,14 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 		s->slab_bytes = off;
 		e = cudaMalloc(&s->slab, s->slab_bytes);
 		if (e != cudaSuccess) { s->slab = nullptr; pft_destroy(s); return fail(PFT_ENOMEM, "cudaMalloc(%zu): %s", s->slab_bytes, cudaGetErrorString(e)); }
-		CU(cudaMemsetAsync(s->slab, 0, s->slab_bytes, s->stream));
+		CUS(cudaMemsetAsync(s->slab, 0, s->slab_bytes, s->stream));
 		for (int a = 0; a < A_COUNT; a++)
 			for (int q = 0; q < 2; q++) s->arr[a][q] = s->off[a][q] ? (double *)(s->slab + s->off[a][q]) : nullptr;
 		s->gl = (double *)(s->slab + s->off_gl);
 		if (!s->heat) { s->arr[A_XN][0] = s->arr[A_X][0]; s->off[A_XN][0] = s->off[A_X][0]; }
 	}
-	CU(cudaMalloc(&s->halo_tickets, 2 * sizeof(unsigned int)));
-	CU(cudaMemsetAsync(s->halo_tickets, 0, 2 * sizeof(unsigned int), s->stream));
+	CUS(cudaMalloc(&s->halo_tickets, 2 * sizeof(unsigned int)));
+	CUS(cudaMemsetAsync(s->halo_tickets, 0, 2 * sizeof(unsigned int), s->stream));
 
 	s->split = s->use_tma && !s->share && env_int("PFT_SPLIT", 0) != 0;
 	if (s->use_tma) {
@@ -788,14 +798,14 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 		int rc = make_tensor_map(s, &s->tmap_gl, s->gl);
 		if (rc) { pft_destroy(s); return rc; }
 	}
-	CU(cudaMalloc(&s->ctl, sizeof(Ctl)));
-	CU(cudaMemsetAsync(s->ctl, 0, sizeof(Ctl), s->stream));
-	CU(cudaMalloc(&s->red, 2 * sizeof(double)));
-	CU(cudaHostAlloc(&s->red_host, 2 * sizeof(double), cudaHostAllocDefault));
-	CU(cudaHostAlloc(&s->slot, sizeof(HostSlot), cudaHostAllocMapped));
+	CUS(cudaMalloc(&s->ctl, sizeof(Ctl)));
+	CUS(cudaMemsetAsync(s->ctl, 0, sizeof(Ctl), s->stream));
+	CUS(cudaMalloc(&s->red, 2 * sizeof(double)));
+	CUS(cudaHostAlloc(&s->red_host, 2 * sizeof(double), cudaHostAllocDefault));
+	CUS(cudaHostAlloc(&s->slot, sizeof(HostSlot), cudaHostAllocMapped));
 	memset(s->slot, 0, sizeof(HostSlot));
-	CU(cudaHostGetDevicePointer(&s->slot_dev, s->slot, 0));
-	CU(cudaStreamSynchronize(s->stream));
+	CUS(cudaHostGetDevicePointer(&s->slot_dev, s->slot, 0));
+	CUS(cudaStreamSynchronize(s->stream));
 
 	memset(&s->st, 0, sizeof s->st);
 	s->st.tile_x = s->TX; s->st.tile_y = s->TY; s->st.z_chunk = g.zc; s->st.threads = s->TX * s->TY;
