@@ -135,12 +135,40 @@ class ClockSampler:
 # the reference CPU path (oracle/_ref when the reference was compiled in the container,
 # else our restatement oracle/pft_oracle.c) -- used by cpu_baseline and by --impl reference
 
-def cpu_reference_run(spec, warmup: int, steps: int):
+class _StdoutToStderr:
+    """The reference's C code prints progress on fd 1; the bench line must be the only thing on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def cpu_reference_run(spec, warmup: int, steps: int, variant: str = "hybrid2", threads: int | None = None):
+    with _StdoutToStderr():
+        return _cpu_reference_run(spec, warmup, steps, variant, threads)
+
+
+def _cpu_reference_run(spec, warmup: int, steps: int, variant: str = "hybrid2", threads: int | None = None):
     """Times `steps` Merson attempts of the reference's own CPU implementation (after `warmup`
-    attempts) with all host threads.  Returns (Mcell-RHS/s, dict describing the run)."""
+    attempts) with all host threads (or `threads`).  variant "hybrid2" = the reference's own flags
+    (-O1), "fast" = the same sources at -O3 -march=x86-64-v3.  Returns (Mcell-RHS/s, attempts,
+    seconds, dict describing the run)."""
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    if threads is not None:       # the OpenMP runtime is already up: change the team size through its API
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
     os.environ.setdefault("OMP_SCHEDULE", "static")      # apps/intertrack-hybrid-S-freezing/Run:13-19
     os.environ.setdefault("OMP_PROC_BIND", "false")
     po.build("oracle")
@@ -149,9 +177,9 @@ def cpu_reference_run(spec, warmup: int, steps: int):
     orc = po.Oracle(case)
     w = case.pack(u, p, gl)
     orc.rasterise(spec.spheres, w)            # OpenMP rasteriser of the restatement (bit-identical to the reference's)
-    if po.have_ref():
+    if po.have_ref(variant):
         kind = "reference"
-        ref = po.Reference()
+        ref = po.Reference(variant)
         gl_r = case.interior(w)[2]
         ref.setup(case, u, p, gl_r, None, t0=0.0, tau=spec.tau, tau_min=spec.tau_min, delta=spec.delta, use_callback=True)
         del w
@@ -179,9 +207,13 @@ def cpu_reference_run(spec, warmup: int, steps: int):
         run_attempts(warmup)
     n, dt = run_attempts(steps)
     value = spec.cells * 5.0 * n / dt / 1e6
-    info = {"value": value, "unit": "Mcell-RHS/s", "cores": int(os.environ["OMP_NUM_THREADS"]), "kind": kind,
+    flags = "-O3 -march=x86-64-v3 -fopenmp" if variant == "fast" else "reference flags -O1 -fopenmp"
+    info = {"value": value, "unit": "Mcell-RHS/s", "cores": int(threads if threads is not None else os.environ["OMP_NUM_THREADS"]), "kind": kind,
             "sample": f"{n} Merson attempts (5 RHS each) of {spec.name} {spec.n1}x{spec.n2}x{spec.n3} after {warmup} warm-up attempts, "
-                      f"reference flags -O1 -fopenmp, {dt:.2f} s"}
+                      f"{flags}, {dt:.2f} s"}
+    if threads is not None:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
     return value, n, dt, info
 
 
@@ -402,6 +434,14 @@ def main():
     if rank == 0 and N == 1 and not args.no_cpu_baseline:
         try:
             _, _, _, cpu = cpu_reference_run(spec, 1, args.cpu_steps)
+            # also the aggressive-flags build and one thread, on short samples
+            others = []
+            from oracle import pyoracle as _po
+            if _po.have_ref("fast"):
+                others.append(cpu_reference_run(spec, 1, max(2, args.cpu_steps // 5), variant="fast")[3])
+            if _po.have_ref("hybrid"):      # a second copy of the reference (own globals) for the 1-thread sample
+                others.append(cpu_reference_run(spec, 0, 1, variant="hybrid", threads=1)[3])
+            cpu["others"] = others
         except Exception as e:      # the baseline is reported, never fatal
             cpu = {"value": None, "unit": "Mcell-RHS/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
 

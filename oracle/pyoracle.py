@@ -92,7 +92,7 @@ def load_oracle():
 
 
 def ref_path(variant: str = "hybrid2") -> str:
-    name = "libpft_ref.so" if variant == "hybrid2" else "libpft_ref_hybrid.so"
+    name = {"hybrid2": "libpft_ref.so", "hybrid": "libpft_ref_hybrid.so", "fast": "libpft_ref_fast.so"}[variant]
     return os.path.join(HERE, "_ref", name)
 
 
