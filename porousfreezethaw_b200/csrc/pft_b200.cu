@@ -260,23 +260,18 @@ static void choose_tile(int n1, int n2, int max_threads, int *TX, int *TY)
 	*TX = btx; *TY = bty;
 }
 
+// z-chunks per tile column.  Measured on B200 (profiles/round1_tuning.md, sweeps on 100x100x200,
+// 200x200x50, 200x200x400, 400x400x50): throughput is flat once a launch has 2.5-7 waves of CTAs
+// (1000-3000 at three resident CTAs per SM) and falls off below 7 planes per chunk (two extra planes
+// are fetched per chunk) and below ~2 waves (tail: late CTAs run alone).  So: aim at 4 waves,
+// never below 7 planes per chunk.
 static int choose_chunks(int tiles_xy, int n3, int sms)
 {
-	double best = -1; int bn = 1;
-	for (int nzc = 1; nzc <= n3; nzc++) {
-		int zc = (n3 + nzc - 1) / nzc;
-		if (zc < 4 && nzc > 1) break;
-		int used = (n3 + zc - 1) / zc;           // chunks actually non-empty
-		if (used != nzc) continue;
-		long blocks = (long)tiles_xy * nzc;
-		long waves = (blocks + sms - 1) / sms;
-		double fill = (double)blocks / (double)(waves * sms);
-		double prol = (double)zc / (zc + 2.0);
-		double bal = (double)n3 / ((double)nzc * zc);
-		double score = fill * prol * bal;
-		if (score > best + 1e-9) { best = score; bn = nzc; }
-	}
-	return bn;
+	const long target = (long)(4 * 3 * sms);
+	long nzc = (target + tiles_xy / 2) / tiles_xy;
+	const long most = std::max(1, n3 / 7);
+	nzc = std::max(1L, std::min(nzc, most));
+	return (int)nzc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -735,8 +730,7 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	}
 	const int tile_rows = rpt * s->TY;
 	int tiles_xy = ((cs->n1 + s->TX - 1) / s->TX) * ((cs->n2 + tile_rows - 1) / tile_rows);
-	int ctas_per_sm = std::max(1, 512 / (rpt * s->TX * s->TY));
-	s->nzc = choose_chunks(tiles_xy, cs->n3, prop.multiProcessorCount * ctas_per_sm);
+	s->nzc = choose_chunks(tiles_xy, cs->n3, prop.multiProcessorCount);
 	if (env_int("PFT_ZCHUNKS", 0) > 0) s->nzc = std::min(cs->n3, env_int("PFT_ZCHUNKS", 0));
 	g.zc = (cs->n3 + s->nzc - 1) / s->nzc;
 	s->nzc = (cs->n3 + g.zc - 1) / g.zc;
