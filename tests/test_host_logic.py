@@ -72,3 +72,44 @@ def test_solver_module_return_codes():
     assert rk.RK_MPI_SA_check_NAN() == 0
     assert rk.RK_MPI_SA_cleanup() == 0
 
+
+
+def test_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference: exactly one JSON line on stdout (the reference's own chatter goes to
+    stderr), carrying the keys the measurement contract names"""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "3",
+                        "--workload", "100-GradP"], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mcell-RHS/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["value"] > 0
+    assert d["config"]["workload"] == "100-GradP" and d["config"]["grid"] == [50, 50, 100]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.parametrize("grid", [(100, 100, 200), (200, 200, 50), (200, 200, 400), (50, 50, 100), (24, 20, 6), (400, 400, 50)])
+def test_z_chunking_rule(emu_lib, grid):
+    """choose_chunks (csrc/pft_b200.cu): about four waves of CTAs at three resident CTAs per SM, never
+    fewer than seven planes per chunk (profiles/round1_tuning.md); a block thinner than that is one
+    chunk.  (The emulated device reports 4 SMs; a B200 has 148.)"""
+    from porousfreezethaw_b200.solver import SlabSolver
+    n1, n2, n3 = grid
+    spec = cases.small_case(n1, n2, n3, calc_mode=1)
+    sol = SlabSolver(spec, lib_path=emu_lib)
+    try:
+        st = sol.stats()
+    finally:
+        sol.close()
+    sms = 4
+    tiles = -(-n1 // st["tile_x"]) * -(-n2 // st["tile_y"])
+    nzc = max(1, min((4 * 3 * sms + tiles // 2) // tiles, max(1, n3 // 7)))
+    zc = -(-n3 // nzc)
+    assert st["z_chunk"] == zc, (st["z_chunk"], zc, tiles)
+    assert st["z_chunk"] >= min(7, n3)
+    assert st["grid_blocks"] == tiles * -(-n3 // st["z_chunk"])
