@@ -54,7 +54,17 @@ def make_spec(name: str, nranks: int):
         if not os.path.exists(sph):
             sph = os.path.join(ROOT, "oracle", "_ref", "data", "spheres_positions.txt")
         spec.spheres = np.loadtxt(sph).reshape(-1, 3) if os.path.exists(sph) else cases.synthetic_spheres(200, zmax=1.6)
-        u, p, gl = pfront.initial_fields_from_formulas(spec, pc.icond)
+        if isinstance(pc.options.get("icond_file"), str):        # `set icond_file=...` [`set continue_series`]
+            path = pc.options["icond_file"]
+            if not os.path.isabs(path):
+                path = os.path.join(os.path.dirname(os.path.abspath(name[7:])), path)
+            r = pfront.restart_from_snapshot(spec, path, continue_series=bool(pc.options.get("continue_series")))
+            u, p, gl = r.u, r.p, r.gl
+            spec.extra["t0"] = r.t
+            if r.tau is not None:
+                spec.tau, spec.final_time = r.tau, r.final_time
+        else:
+            u, p, gl = pfront.initial_fields_from_formulas(spec, pc.icond)
         spec.initial_fields = lambda first_row=0, n3_local=None, _f=(u, p, gl), _s=spec: tuple(
             a[first_row:first_row + (_s.n3 if n3_local is None else n3_local)] for a in _f)
         return spec, "strong", f"case file {name[7:]}"
@@ -294,6 +304,7 @@ def main():
     sol.upload_interior(u, p, gl)
     sol.rasterise(spec.spheres)
     del u, p, gl
+    sol.sys.t, sol.sys.h = float(spec.extra.get("t0", 0.0)), spec.tau      # a restart dataset may set both
 
     def barrier():
         torch.cuda.synchronize()

@@ -244,3 +244,47 @@ def initial_fields_from_formulas(spec: CaseSpec, formulas: dict, first_row: int 
     if len(done) != len(names):
         raise ExprError(f"cannot evaluate initial conditions for {[n for n in names if n not in done]}")
     return done["u"], done["p"], done["gl"]
+
+
+@dataclass
+class Restart:
+    """what `set icond_file=...` [`set continue_series`] hands to a run (intertrack.c:1585-1669, 2036-2110)"""
+    u: np.ndarray
+    p: np.ndarray
+    gl: np.ndarray
+    t: float = 0.0
+    tau: float | None = None
+    final_time: float | None = None
+    snapshot: int = 0
+    total_snapshots: int | None = None
+
+
+def restart_from_snapshot(spec: CaseSpec, path: str, continue_series: bool = False, first_row: int = 0,
+                          n3_local: int | None = None) -> Restart:
+    """Initial fields of rows [first_row, first_row+n3_local) from a snapshot dataset (NetCDF classic
+    or the PFTSNAP container), as the reference loads its `icond_file`: the dataset's dimensions must
+    equal the case's grid (intertrack.c:1601-1633); with `continue_series` the starting time, the
+    step size, final_time and the snapshot numbering are taken from the dataset's attributes
+    (:1642-1669), and the dataset must carry them."""
+    from . import snapshot as sn
+    with open(path, "rb") as f:
+        magic = f.read(10)
+    ds = sn.read_snapshot(path) if magic == sn.MAGIC else sn.read_netcdf(path)
+    want = {"n1": spec.n1, "n2": spec.n2, "n3": spec.n3}
+    for d, n in want.items():
+        if ds["dims"].get(d) != n:
+            raise ExprError(f"{path}: dimension {d} is {ds['dims'].get(d)}, the case has {n}")
+    for v in ("u", "p", "gl"):
+        if v not in ds["vars"] or ds["vars"][v].shape != (spec.n3, spec.n2, spec.n1):
+            raise ExprError(f"{path}: variable {v} missing or not double[n3][n2][n1]")
+    n3l = spec.n3 if n3_local is None else n3_local
+    rows = slice(first_row, first_row + n3l)
+    r = Restart(*(np.ascontiguousarray(ds["vars"][v][rows], dtype=np.float64) for v in ("u", "p", "gl")))
+    if continue_series:
+        a = ds["attrs"]
+        missing = [k for k in ("snapshot", "total_snapshots", "t", "final_time", "tau") if k not in a]
+        if missing:
+            raise ExprError(f"{path}: continue_series needs the attributes {missing}")
+        r.t, r.tau, r.final_time = float(a["t"]), float(a["tau"]), float(a["final_time"])
+        r.snapshot, r.total_snapshots = int(a["snapshot"]), int(a["total_snapshots"])
+    return r

@@ -110,3 +110,25 @@ def test_reference_application_snapshot_converts(tmp_path):
         got = getattr(f, k)
         assert (got.decode() if isinstance(got, bytes) else got) == v, k
     f.close()
+
+
+def test_restart_input_from_either_container(tmp_path):
+    """`set icond_file` / `set continue_series` (intertrack.c:1585-1669, 2036-2110) in the Params front end"""
+    from porousfreezethaw_b200 import cases, params
+    spec = cases.small_case(6, 5, 9, calc_mode=1)
+    u, p, gl = _fields((9, 5, 6), seed=21)
+    attrs = {"t": 123.5, "tau": 0.25, "final_time": 36000.0, "snapshot": 17, "total_snapshots": 100, "calc_mode": 1}
+    sn.write_snapshot(str(tmp_path / "image.017.ncd"), u, p, gl, (spec.L1, spec.L2, spec.L3), attrs, title="t")
+    sn.convert(str(tmp_path / "image.017.ncd"), str(tmp_path / "image.017.nc"))
+    for path in ("image.017.ncd", "image.017.nc"):
+        r = params.restart_from_snapshot(spec, str(tmp_path / path))
+        assert np.array_equal(r.u, u) and np.array_equal(r.p, p) and np.array_equal(r.gl, gl)
+        assert (r.t, r.tau, r.snapshot) == (0.0, None, 0)                    # plain icond_file: fields only
+        r = params.restart_from_snapshot(spec, str(tmp_path / path), continue_series=True, first_row=3, n3_local=4)
+        assert np.array_equal(r.p, p[3:7]) and r.u.flags["C_CONTIGUOUS"]      # one rank's block (:2046-2062)
+        assert (r.t, r.tau, r.final_time, r.snapshot, r.total_snapshots) == (123.5, 0.25, 36000.0, 17, 100)
+    with pytest.raises(params.ExprError):
+        params.restart_from_snapshot(cases.small_case(6, 5, 8, calc_mode=1), str(tmp_path / "image.017.nc"))
+    sn.write_snapshot(str(tmp_path / "bare.ncd"), u, p, gl, (1, 1, 1), {"t": 1.0}, title="")
+    with pytest.raises(params.ExprError):
+        params.restart_from_snapshot(spec, str(tmp_path / "bare.ncd"), continue_series=True)
