@@ -276,9 +276,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; porousfreezethaw_b200 has no CPU path")
-    torch.cuda.set_device(local)
+    # TEST INFRASTRUCTURE ONLY (tests/test_host_logic.py): walk through this script on a machine without a
+    # GPU against the CPU emulation of the CUDA sources (tests/cuda_emu), to check the line it prints.
+    # The line says so in "data"; nothing measured that way is a benchmark.
+    dry = os.environ.get("PFT_BENCH_DRYRUN_LIB")
+    if dry:
+        if world != 1:
+            raise SystemExit("bench.py: the dry run is single-rank")
+        print("bench.py: DRY RUN against the CPU emulation (PFT_BENCH_DRYRUN_LIB) -- test of this script, not a measurement",
+              file=sys.stderr)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; porousfreezethaw_b200 has no CPU path")
+        torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -291,6 +301,8 @@ def main():
     lib_path = _pftlib.FAST_LIB_PATH if args.variant == "fast" else None
     if os.environ.get("PFT_BENCH_LIB"):       # A/B builds (development)
         lib_path = os.environ["PFT_BENCH_LIB"]
+    if dry:
+        lib_path = dry
     sol = SlabSolver(spec, rank=rank, nranks=N, device=local, lib_path=lib_path)
     if N > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -307,6 +319,8 @@ def main():
     sol.sys.t, sol.sys.h = float(spec.extra.get("t0", 0.0)), spec.tau      # a restart dataset may set both
 
     def barrier():
+        if dry:
+            return
         torch.cuda.synchronize()
         if N > 1:
             dist.barrier()
@@ -357,6 +371,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     st1 = sol.stats()
     dev_ms = allmax(my_ms)                                   # max over ranks
+    if dry and dev_ms <= 0:
+        dev_ms = 1e3 * t_wall                                # the emulation has no device clock
     attempts = st1["attempts"] - st0["attempts"]
     rhs = sol.sys.rhs_evals - ev0
     total_cells = allsum(float(sol.cells))
@@ -402,6 +418,8 @@ def main():
         if nl == 0:
             continue
         ms = stp["stage_ms"][i] / nl
+        if dry and ms <= 0:
+            ms = 1e-3
         gbs = sol.cells * sb[i] / (ms * 1e-3) / 1e9
         stages.append({"stage": i + 1, "launches": nl, "avg_ms": ms, "bytes_per_cell": sb[i], "achieved_gbs": gbs, "frac": gbs / peak})
     dom = max(stages, key=lambda s: s["avg_ms"] * s["launches"])
@@ -422,7 +440,7 @@ def main():
     solp.close()
 
     # ---- end to end: pinned HOST buffers -> upload -> K attempts -> download ---------------
-    xh = torch.empty(3 * sol.SIZE, dtype=torch.float64, pin_memory=True).numpy()
+    xh = np.empty(3 * sol.SIZE) if dry else torch.empty(3 * sol.SIZE, dtype=torch.float64, pin_memory=True).numpy()
     sol.download(xh)                                         # a valid padded host image of the current state
     barrier()
     ev0 = sol.sys.rhs_evals
@@ -461,7 +479,8 @@ def main():
         line = {
             "metric": "Mcell-RHS evals/s", "value": value, "unit": "Mcell-RHS/s", "n_gpus": N,
             "steps": attempts, "warmup": args.warmup, "ms_per_step": dev_ms / max(attempts, 1),
-            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "DRY RUN on the CPU emulation (tests only): not a measurement" if dry else "synthetic",
             "config": {"workload": spec.name, "grid": [spec.n1, spec.n2, spec.n3], "calc_mode": spec.calc_mode,
                        "geometry": geo, "mode": f"fixed step H={H:.6g}" if args.fixed_step else "adaptive (delta 1e-3)", "variant": args.variant, "cache": "inputs larger than L2 (no flush needed)"
                        if sol.cells * 13 * 8 > 2 * 126e6 else "working set fits L2",

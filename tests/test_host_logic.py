@@ -113,3 +113,31 @@ def test_z_chunking_rule(emu_lib, grid):
     assert st["z_chunk"] == zc, (st["z_chunk"], zc, tiles)
     assert st["z_chunk"] >= min(7, n3)
     assert st["grid_blocks"] == tiles * -(-n3 // st["z_chunk"])
+
+
+@pytest.mark.parametrize("extra", [[], ["--fixed-step"]])
+def test_bench_line_schema_dry_run(emu_lib, extra):
+    """bench.py walked through end to end against the CPU emulation (PFT_BENCH_DRYRUN_LIB): one JSON line
+    with every key of the measurement contract.  The values mean nothing (the line says so)."""
+    import json
+    import sys
+    env = dict(os.environ, PFT_BENCH_DRYRUN_LIB=emu_lib)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--workload", "slab-24x16",
+                        "--profile-steps", "2", "--cpu-steps", "2", *extra], capture_output=True, text=True, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert "DRY RUN" in d["data"]
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "Mcell-RHS/s" and d["dtype"] == "f64" and d["n_gpus"] == 1 and d["steps"] == 3 and d["vs_baseline"] is None
+    assert d["config"]["workload"] and "model" not in d["config"]
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"]) and d["roofline"]["bound"] == "hbm"
+    assert len(d["roofline"]["per_stage"]) == 5 and [s["bytes_per_cell"] for s in d["roofline"]["per_stage"]] == [40, 56, 40, 72, 88]
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+    # 5 stage kernels per attempt: 4 + the speculative stage 1 of the next step
+    assert d["gpu_launches"] == 5 * 3
+    assert ("fixed step" in d["config"]["mode"]) == bool(extra)
