@@ -333,7 +333,8 @@ template <int STAGE, int MODEL, bool HEAT, bool SHARE>
 static cudaError_t launch_t(pft_solver *s, const KParams &kp)
 {
 	auto fn = merson_stage<STAGE, MODEL, HEAT, SHARE>;
-	static bool attr_set = false;
+	static bool attr_set_dev[64] = {};        // the attribute is per device (and per template instance)
+	bool &attr_set = attr_set_dev[s->device & 63];
 	if (!attr_set) {
 		cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 		if (e != cudaSuccess) return e;
@@ -359,7 +360,8 @@ template <int STAGE, int MODEL, bool SHARE, bool SPLIT>
 static cudaError_t launch_tma_t(pft_solver *s, const TmaParams &kp)
 {
 	auto fn = merson_stage_tma<STAGE, MODEL, SHARE, SPLIT>;
-	static bool attr_set = false;
+	static bool attr_set_dev[64] = {};        // the attribute is per device (and per template instance)
+	bool &attr_set = attr_set_dev[s->device & 63];
 	if (!attr_set) {
 		cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
 		if (e != cudaSuccess) return e;
@@ -373,7 +375,8 @@ template <int STAGE, int MODEL>
 static cudaError_t launch_tma2_t(pft_solver *s, const TmaParams &kp)
 {
 	auto fn = merson_stage_tma2<STAGE, MODEL>;
-	static bool attr_set = false;
+	static bool attr_set_dev[64] = {};        // the attribute is per device (and per template instance)
+	bool &attr_set = attr_set_dev[s->device & 63];
 	if (!attr_set) {
 		cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
 		if (e != cudaSuccess) return e;
