@@ -264,7 +264,9 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=40)
     args = ap.parse_args()
     if args.warmup < 3:
-        args.warmup = 3
+        args.warmup = 3          # the timing rules ask for W >= 3 (and 0 would mean "no attempt limit" to pft_solve)
+    if args.steps < 1:
+        args.steps = 1
 
     if args.impl == "reference":
         return run_reference_arm(args)
