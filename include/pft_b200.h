@@ -23,6 +23,8 @@
  *                              (equation.c:566-741, :745-884) incl. bcond_setup (:266-284)
  *   pft_solve                  RK_MPI_SA_solve (RK_MPI_SAsolver_hybrid2.c:215-770; twin
  *                              modules/RK_MPI_SAsolver_hybrid/RK_MPI_SAsolver_hybrid.c)
+ *   pft_group_*                the same for one host process that owns several GPUs: the z-slab partition of
+ *                              intertrack.c:1776-1800 applied inside the solver module
  *   pft_comm_*                 the z-halo exchange sync_solution (equation.c:290-326) and
  *                              MPI_Allreduce(MAX) (RK_MPI_SAsolver_hybrid2.c:572)
  *   pft_rasterise              the sphere rasteriser of PrecalculateData (equation.c:474-529)
@@ -56,13 +58,21 @@ extern "C" {
 #define PFT_SOLVE_NAN        (-4)  /* RK_MPI_SA_solve: -4 */
 
 /* flags for pft_create */
-#define PFT_FLAG_NO_FLUX_SHARING  1u   /* every cell computes its six face fluxes itself (the default) */
-#define PFT_FLAG_NO_SPECULATION   2u   /* do not launch the next K1 before the step-size decision */
+#define PFT_FLAG_NO_RUNAHEAD      2u   /* enqueue one attempt at a time and wait for its outcome (default: the host
+                                          enqueues attempts ahead of the device, which decides by itself) */
 #define PFT_FLAG_RECOMPUTE_K1     4u   /* recompute K1 after a rejected attempt, like the reference */
 #define PFT_FLAG_LEGACY_LOADS     8u   /* per-thread global loads instead of TMA tile staging (debug / A-B) */
-#define PFT_FLAG_FLUX_SHARING    16u   /* cells exchange face fluxes through shared memory (A-B; costs a second CTA barrier) */
+#define PFT_FLAG_HOST_POW        32u   /* take pow(delta/eps, 0.2) of the step-size controller from the host C library
+                                          once per attempt instead of the device twin of it (checker for the twin) */
+
+/* field masks for pft_upload_fields / pft_download_fields */
+#define PFT_FIELD_U   1u
+#define PFT_FIELD_P   2u
+#define PFT_FIELD_GL  4u
+#define PFT_FIELD_ALL 7u
 
 typedef struct pft_solver pft_solver;
+typedef struct pft_group pft_group;      /* several z-slabs of one grid on several GPUs, driven by ONE host process */
 
 /* one block (z-slab) of the grid; field meaning as in intertrack.c */
 typedef struct {
@@ -105,8 +115,13 @@ typedef struct {
 	long   stage_launches[5];
 	int    tile_x, tile_y, z_chunk, threads, grid_blocks;
 	long   bytes_per_field;  /* device bytes of one field array incl. ghost planes */
-	double host_wait_ms;     /* host time spent waiting for the device's step decision */
+	double host_wait_ms;     /* host time spent waiting (asleep, not spinning) for the device to free a slot of
+	                            the launch queue */
 	double host_launch_ms;   /* host time spent issuing launches */
+	int    device_pow;       /* 1: the step-size controller runs on the device with the twin of the host library's
+	                            pow(); 0: the host supplies pow() once per attempt (twin unavailable or PFT_FLAG_HOST_POW) */
+	int    runahead;         /* attempts the host keeps enqueued ahead of the device */
+	long   noop_launches;    /* stage launches that found the integration already finished (run-ahead tail) */
 } pft_stats;
 
 const char *pft_last_error(void);
@@ -118,6 +133,13 @@ int pft_destroy(pft_solver *s);
 /* host array in the reference's padded layout: 3 * N1*N2*N3 doubles, N_d = n_d + 2*PFT_BT */
 int pft_upload(pft_solver *s, const double *x_padded);
 int pft_download(pft_solver *s, double *x_padded);          /* writes interior nodes only */
+/* the same for a subset of the variables (PFT_FIELD_*): the glass field is static (dgl/dt == 0, equation.c:731),
+ * so a caller that keeps one host array across solve calls uploads it once and never downloads it */
+int pft_upload_fields(pft_solver *s, const double *x_padded, unsigned mask);
+int pft_download_fields(pft_solver *s, double *x_padded, unsigned mask);
+/* page-lock a caller-owned host array so that the copies above run at full PCIe speed (optional) */
+int pft_host_register(void *ptr, unsigned long long bytes);
+int pft_host_unregister(void *ptr);
 /* compact interior arrays [n3][n2][n1]; any pointer may be NULL to skip that field */
 int pft_upload_interior(pft_solver *s, const double *u, const double *p, const double *gl);
 int pft_download_interior(pft_solver *s, double *u, double *p, double *gl);
@@ -139,18 +161,29 @@ int pft_ice_fraction(pft_solver *s, double *fraction);
 int pft_comm_unique_id(void *id128);
 int pft_comm_init(pft_solver *s, const void *id128);
 
+/* multi-GPU, ONE host process driving ngpus devices (one worker thread per device inside pft_group_solve):
+ * what the reference does with M MPI ranks inside one application run (intertrack.c:1776-1800 slab partition,
+ * equation.c:290-326 halo exchange, RK_MPI_SAsolver_hybrid2.c:572 error maximum).  `whole` describes the WHOLE
+ * block this process owns (rank 0 of 1); it is cut into ngpus z-slabs by the rule of intertrack.c:1780-1787.
+ * The slabs reach each other through peer access (NVLink), no NCCL.  x_padded is the one padded host array of
+ * the whole block; the service callback is invoked by slab 0's worker only. */
+int pft_group_create(const pft_case *whole, int ngpus, const int *devices, unsigned flags, pft_group **out);
+int pft_group_destroy(pft_group *g);
+int pft_group_size(const pft_group *g);
+pft_solver *pft_group_member(pft_group *g, int r);
+int pft_group_upload(pft_group *g, const double *x_padded, unsigned mask);
+int pft_group_download(pft_group *g, double *x_padded, unsigned mask);
+int pft_group_solve(pft_group *g, pft_system *sys, double final_time);
+
+/* test hook: n values x[i]^y of the DEVICE instance of the step-size controller's pow twin (pft_pow.h) */
+int pft_debug_pow(pft_solver *s, const double *x, double y, double *out, int n);
+
 int pft_get_stats(pft_solver *s, pft_stats *out);
 int pft_reset_stats(pft_solver *s);
 
 /* debug/test hook: copy an internal array pair (u,p components) to compact host arrays.
  * which: 0 x, 1 K1, 2 aux3 (stage-3 input), 3 K3, 4 K4, 5 x_new (last attempt's candidate) */
 int pft_debug_fetch(pft_solver *s, int which, double *u, double *p);
-/* development builds only (-DPFT_TRACE, libpft_b200_trace.so): device timeline of the stage launches since
- * the last call, 16 uint64 per launch (layout: csrc/pft_kernels.cuh); returns the record count */
-int pft_debug_trace(pft_solver *s, unsigned long long *records, int *stages, int max_records);
-/* same builds: per-CTA (start, end of body, end, smid<<32|chunk) of the first 12 launches since the last
- * pft_debug_trace call, 1024 CTAs x 4 uint64 per launch; returns the number of launches copied */
-int pft_debug_trace_cta(pft_solver *s, unsigned long long *out, int launches);
 
 #ifdef __cplusplus
 }

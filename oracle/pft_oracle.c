@@ -474,3 +474,12 @@ double pfo_ice_fraction(const pfo_case *c, const double *w)
 				if (p[(size_t)(k + PFO_BT) * g.rowsize + (size_t)(j + PFO_BT) * g.N1 + PFO_BT + i] > 0.5) cnt++;
 	return (double)cnt / ((double)c->n1 * c->n2 * c->n3);
 }
+
+/* the C library's pow() on an array: the reference's step-size controller calls exactly this function
+ * (RK_MPI_SAsolver_hybrid2.c:580); the tests hold the device twin (csrc/pft_pow.h) against it */
+void pfo_pow_array(const double *x, double y, double *out, long n)
+{
+	long i;
+	#pragma omp parallel for schedule(static)
+	for (i = 0; i < n; i++) out[i] = pow(x[i], y);
+}

@@ -97,6 +97,9 @@ int  pfo_solve(const pfo_case *c, pfo_system *s, double *x, double *work, double
 /* mean(p > 0.5) over the interior: what scripts/avg.sh:9-20 computes with NCO */
 double pfo_ice_fraction(const pfo_case *c, const double *w);
 
+/* out[i] = pow(x[i], y) with the C library's pow (what RK_MPI_SAsolver_hybrid2.c:580 calls) */
+void pfo_pow_array(const double *x, double y, double *out, long n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,8 +87,17 @@ def load_oracle():
         lib.pfo_solve.restype = C.c_int
         lib.pfo_ice_fraction.argtypes = [C.POINTER(_CCase), _dp]
         lib.pfo_ice_fraction.restype = C.c_double
+        lib.pfo_pow_array.argtypes = [_dp, C.c_double, _dp, C.c_long]
         _oracle_lib = lib
     return _oracle_lib
+
+
+def libm_pow(x: np.ndarray, y: float) -> np.ndarray:
+    """x**y with the C library's pow(), element by element (NOT numpy's vectorised power)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    load_oracle().pfo_pow_array(_ptr(x), float(y), _ptr(out), x.size)
+    return out
 
 
 def ref_path(variant: str = "hybrid2") -> str:

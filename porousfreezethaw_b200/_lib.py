@@ -10,7 +10,6 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libpft_b200.so")
 RK_LIB_PATH = os.path.join(HERE, "csrc", "librk_b200.so")
-TRACE_LIB_PATH = os.path.join(HERE, "csrc", "libpft_b200_trace.so")    # development: device timeline records
 FAST_LIB_PATH = os.path.join(HERE, "csrc", "libpft_b200_fast.so")      # opt-in FMA variant (not bit-exact)
 
 NPARAM = 30
@@ -42,7 +41,8 @@ class PftStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_long), ("rhs_evals", C.c_long), ("attempts", C.c_long), ("accepted", C.c_long),
                 ("device_ms_total", C.c_double), ("stage_ms", C.c_double * 5), ("stage_launches", C.c_long * 5),
                 ("tile_x", C.c_int), ("tile_y", C.c_int), ("z_chunk", C.c_int), ("threads", C.c_int), ("grid_blocks", C.c_int),
-                ("bytes_per_field", C.c_long), ("host_wait_ms", C.c_double), ("host_launch_ms", C.c_double)]
+                ("bytes_per_field", C.c_long), ("host_wait_ms", C.c_double), ("host_launch_ms", C.c_double),
+                ("device_pow", C.c_int), ("runahead", C.c_int), ("noop_launches", C.c_long)]
 
 
 # every symbol include/pft_b200.h declares
@@ -50,7 +50,9 @@ EXPORTS = [
     "pft_last_error", "pft_version", "pft_create", "pft_destroy", "pft_upload", "pft_download",
     "pft_upload_interior", "pft_download_interior", "pft_rasterise", "pft_rhs_host", "pft_solve",
     "pft_ice_fraction", "pft_comm_unique_id", "pft_comm_init", "pft_get_stats", "pft_reset_stats",
-    "pft_debug_fetch", "pft_debug_trace", "pft_debug_trace_cta",
+    "pft_debug_fetch", "pft_debug_pow", "pft_upload_fields", "pft_download_fields", "pft_host_register", "pft_host_unregister",
+    "pft_group_create", "pft_group_destroy", "pft_group_size", "pft_group_member", "pft_group_upload", "pft_group_download",
+    "pft_group_solve",
 ]
 
 _cache: dict[str, C.CDLL] = {}
@@ -85,8 +87,19 @@ def load(path: str | None = None) -> C.CDLL:
     lib.pft_get_stats.argtypes = [vp, C.POINTER(PftStats)]
     lib.pft_reset_stats.argtypes = [vp]
     lib.pft_debug_fetch.argtypes = [vp, C.c_int, _dp, _dp]
-    lib.pft_debug_trace_cta.argtypes = [vp, C.POINTER(C.c_ulonglong), C.c_int]
-    lib.pft_debug_trace.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_int), C.c_int]
+    lib.pft_debug_pow.argtypes = [vp, _dp, C.c_double, _dp, C.c_int]
+    lib.pft_upload_fields.argtypes = [vp, _dp, C.c_uint]
+    lib.pft_download_fields.argtypes = [vp, _dp, C.c_uint]
+    lib.pft_host_register.argtypes = [C.c_void_p, C.c_ulonglong]
+    lib.pft_host_unregister.argtypes = [C.c_void_p]
+    lib.pft_group_create.argtypes = [C.POINTER(PftCase), C.c_int, C.POINTER(C.c_int), C.c_uint, C.POINTER(vp)]
+    lib.pft_group_destroy.argtypes = [vp]
+    lib.pft_group_size.argtypes = [vp]
+    lib.pft_group_member.argtypes = [vp, C.c_int]
+    lib.pft_group_member.restype = vp
+    lib.pft_group_upload.argtypes = [vp, _dp, C.c_uint]
+    lib.pft_group_download.argtypes = [vp, _dp, C.c_uint]
+    lib.pft_group_solve.argtypes = [vp, C.POINTER(PftSystem), C.c_double]
     for name in EXPORTS:
         getattr(lib, name)
     _cache[path] = lib

@@ -1,17 +1,17 @@
 // pft_b200.cu -- C ABI (include/pft_b200.h) over the sm_100a kernels of pft_kernels.cuh.
 //
-// Host side of the Runge-Kutta-Merson integrator.  The control flow restates
-// modules/RK_MPI_SAsolver_hybrid2/RK_MPI_SAsolver_hybrid2.c:215-770 of the reference for a
+// Host side of the Runge-Kutta-Merson integrator
+// (modules/RK_MPI_SAsolver_hybrid2/RK_MPI_SAsolver_hybrid2.c:215-770 of the reference) for a
 // device-resident state:
 //   * the five RHS evaluations and all vector combinations run as five fused stage kernels;
-//   * the step-size controller stays on the host because it needs glibc's pow() to reproduce the
-//     reference's accepted-step sequence bit for bit (the device publishes the error max into a
-//     pinned, mapped slot; the host spins on its sequence number);
-//   * while the host decides, the device already evaluates K1 of the NEXT step from the
-//     candidate x_new, gated on the accept flag the last CTA of stage 5 computed (the accept
-//     test itself is an exact comparison, only the new step length needs pow);
+//   * the step-size controller runs on the DEVICE too (pft_ctl.h: one thread of stage 5's last CTA),
+//     with a twin of the host C library's pow() that is checked against that library at start-up
+//     (pft_pow.h), so the accepted-step sequence is the reference's bit for bit;
+//   * every scalar a stage needs is read from the device-resident control block, so the launches of
+//     an attempt do not depend on the previous outcome: the host enqueues attempts ahead of the
+//     device and sleeps on a progress slot -- no host round trip and no host spin in the time loop;
 //   * after a rejected attempt K1 is reused (x and t did not change), which the reference
-//     recomputes needlessly (:373).
+//     recomputes needlessly (:373): stage 1 of the next attempt returns at once.
 //
 // This file is compiled with -fmad=false and the host compiler with -ffp-contract=off: every
 // floating-point expression keeps the reference's association.
@@ -20,7 +20,6 @@
 #include "pft_kernels_tma.cuh"
 
 #include <dlfcn.h>
-#include <emmintrin.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -29,7 +28,11 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include <nccl.h>
@@ -81,9 +84,9 @@ static int fail(int code, const char *fmt, ...)
 
 extern "C" const char *pft_last_error(void) { return g_err; }
 #ifdef PFT_FAST_FP
-extern "C" const char *pft_version(void) { return "pft-b200 0.1 (sm_100a, float64, FAST variant: FMA contraction allowed, not bit-exact)"; }
+extern "C" const char *pft_version(void) { return "pft-b200 0.2 (sm_100a, float64, FAST variant: FMA contraction allowed, not bit-exact)"; }
 #else
-extern "C" const char *pft_version(void) { return "pft-b200 0.1 (sm_100a, float64, strict IEEE association)"; }
+extern "C" const char *pft_version(void) { return "pft-b200 0.2 (sm_100a, float64, strict IEEE association)"; }
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -160,8 +163,6 @@ struct pft_solver {
 	Geom g;
 	int model;            // 0,1,2
 	bool heat;
-	bool share;
-	bool speculate, speculate_req;
 	int TX, TY, nzc;
 	dim3 grid, block;
 	size_t smem;
@@ -169,16 +170,21 @@ struct pft_solver {
 	double *arr[A_COUNT][2];   // [pair][u|p]
 	double *gl;
 	double *stage_buf;    // padded-layout staging (3*SIZE doubles)
+	bool stage_shell[PFT_NVAR];  // the staging image of that variable holds the ghost shell of the caller's host array
 	long long padded;     // 3*SIZE
 	int N1, N2, N3;
-	Ctl *ctl;
-	double *red;          // device: {eps, nonfinite} of the last stage 5 (multi-GPU reduction input)
-	double *red_host;     // pinned copy
-	HostSlot *slot;       // pinned + mapped
+	// device-resident step control (pft_ctl.h)
+	StepCtl *ctl;         // device
+	StepCtl *ctl_host;    // pinned: staging of the block the host writes at solve entry
+	HostSlot *slot;       // pinned + mapped: progress slot written by the controller thread
 	HostSlot *slot_dev;   // device alias
-	unsigned long long seq;
+	PowTables *tab_dev;   // device copy of the host library's pow tables (nullptr: host pow)
+	bool dev_pow;
+	int cur;              // which state pair holds x at rest (mirror of StepCtl.cur)
+	unsigned long long aseq;   // attempts started on this solver so far (mirror of StepCtl.aseq at rest)
+	int depth;            // attempts the host keeps enqueued ahead of the device
 	cudaStream_t stream;
-	cudaEvent_t ev0, ev1, ev_red;
+	cudaEvent_t ev0, ev1;
 	bool k1_valid;
 	double k1_t;
 	ncclComm_t comm;
@@ -187,37 +193,40 @@ struct pft_solver {
 	bool pdl;             // stage kernels use programmatic dependent launch (off while profiling stages)
 	std::vector<StageTimer> timers;
 	pft_stats st;
-	// one device slab: [SyncBlock][13 field arrays]; peers map it with CUDA IPC
+	// one device slab: [SyncBlock][13 field arrays]; peers map it (CUDA IPC between processes, peer access inside one)
 	char *slab;
 	size_t slab_bytes;
 	size_t off[A_COUNT][2], off_gl;            // byte offsets of the arrays inside the slab (same on every rank)
 	// peer path (multi-GPU without NCCL in the time loop)
 	bool p2p;
+	bool ipc;                                  // peer_base[] came from cudaIpcOpenMemHandle
 	char *peer_base[PFT_MAX_RANKS];            // every rank's slab in this process' address space
 	int peer_n3[PFT_MAX_RANKS];
 	unsigned int *halo_tickets;
-	unsigned long long hseq;                   // stage-launch sequence number (identical on all ranks)
+	pft_group *group;                          // member of an in-process group (pft_group_*)
 	// TMA path (heat modes): one tensor map per array, box = tile + halo ring
 	bool use_tma;
-	bool split;           // split-phase mbarriers instead of a CTA barrier per plane
-	bool rows2;           // two vertically adjacent cells per thread (merson_stage_tma2)
 	CUtensorMap tmap[A_COUNT][2];
 	CUtensorMap tmap_gl;
 	int bx, by, as;
 	size_t smem_tma[5];
-	// development build (-DPFT_TRACE): device timeline records, 16 x u64 per stage launch
-	unsigned long long *trace, *trace_cta;
-	std::vector<int> trace_stage;
+	// launch arguments of the five stages: independent of the step length and of earlier outcomes (pft_ctl.h)
+	bool params_ok;
+	KParams kp[5];
+	TmaParams tp[5];
 };
-#ifdef PFT_TRACE
-constexpr int TRACE_CAP = 4096, TRACE_REC = 16, TRACE_CTA_LAUNCHES = 12;
-#endif
 
-static double dirichlet(const pft_solver *s, double t)
-{
-	// equation.c:96-111
-	return t < s->cs.param[P_phase_switch_time] ? s->cs.param[P_top_temp1] : s->cs.param[P_top_temp2];
-}
+// one host process, several GPUs: slab r of the block lives on devices[r]
+struct pft_group {
+	int n;
+	pft_case whole;
+	std::vector<pft_solver *> member;
+	// service callback agreement: slab 0's worker calls the user's callback, the others take its verdict
+	pft_service_fn user_service;
+	void *user_ctx;
+	std::atomic<long> cb_seq;
+	std::atomic<int> cb_val;
+};
 
 static int env_int(const char *name, int dflt)
 {
@@ -329,10 +338,36 @@ static void make_consts(pft_solver *s)
 	c.g_lam = p[P_glass_lambda]; c.i_lam = p[P_ice_lambda]; c.w_lam = p[P_water_lambda];
 }
 
-template <int STAGE, int MODEL, bool HEAT, bool SHARE>
+// ------------------------------------------------------------------------------------------
+// the host library's pow tables (pft_pow.h): loaded and checked once per process
+
+struct PowGate {
+	PowTables tab;
+	bool usable = false;
+	char why[256] = "";
+};
+
+static const PowGate &pow_gate()
+{
+	static PowGate g;
+	static std::once_flag once;
+	std::call_once(once, []() {
+		if (env_int("PFT_HOST_POW", 0)) { snprintf(g.why, sizeof g.why, "disabled by PFT_HOST_POW"); return; }
+		if (pft_pow_load_tables(&g.tab, g.why, sizeof g.why)) return;
+		const long bad = pft_pow_selftest(g.tab, 0.2, 400000, 0x5eedull);
+		if (bad) { snprintf(g.why, sizeof g.why, "the twin differs from the C library's pow() on %ld of 400000 operands", bad); return; }
+		g.usable = true;
+	});
+	return g;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage launch
+
+template <int STAGE, int MODEL, bool HEAT>
 static cudaError_t launch_t(pft_solver *s, const KParams &kp)
 {
-	auto fn = merson_stage<STAGE, MODEL, HEAT, SHARE>;
+	auto fn = merson_stage<STAGE, MODEL, HEAT>;
 	static bool attr_set_dev[64] = {};        // the attribute is per device (and per template instance)
 	bool &attr_set = attr_set_dev[s->device & 63];
 	if (!attr_set) {
@@ -347,34 +382,15 @@ static cudaError_t launch_t(pft_solver *s, const KParams &kp)
 template <int STAGE>
 static cudaError_t launch_stage_t(pft_solver *s, const KParams &kp)
 {
-	if (s->model == 2) return s->share ? launch_t<STAGE, 2, true, true>(s, kp) : launch_t<STAGE, 2, true, false>(s, kp);
-	if (s->model == 0) {
-		if (s->heat) return s->share ? launch_t<STAGE, 0, true, true>(s, kp) : launch_t<STAGE, 0, true, false>(s, kp);
-		return launch_t<STAGE, 0, false, false>(s, kp);
-	}
-	if (s->heat) return s->share ? launch_t<STAGE, 1, true, true>(s, kp) : launch_t<STAGE, 1, true, false>(s, kp);
-	return launch_t<STAGE, 1, false, false>(s, kp);
-}
-
-template <int STAGE, int MODEL, bool SHARE, bool SPLIT>
-static cudaError_t launch_tma_t(pft_solver *s, const TmaParams &kp)
-{
-	auto fn = merson_stage_tma<STAGE, MODEL, SHARE, SPLIT>;
-	static bool attr_set_dev[64] = {};        // the attribute is per device (and per template instance)
-	bool &attr_set = attr_set_dev[s->device & 63];
-	if (!attr_set) {
-		cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-		if (e != cudaSuccess) return e;
-		attr_set = true;
-	}
-	PFT_LAUNCH_PDL(s->pdl, fn, s->grid, s->block, s->smem_tma[STAGE - 1], s->stream, kp);
-	return cudaGetLastError();
+	if (s->model == 2) return launch_t<STAGE, 2, true>(s, kp);
+	if (s->model == 0) return s->heat ? launch_t<STAGE, 0, true>(s, kp) : launch_t<STAGE, 0, false>(s, kp);
+	return s->heat ? launch_t<STAGE, 1, true>(s, kp) : launch_t<STAGE, 1, false>(s, kp);
 }
 
 template <int STAGE, int MODEL>
-static cudaError_t launch_tma2_t(pft_solver *s, const TmaParams &kp)
+static cudaError_t launch_tma_t(pft_solver *s, const TmaParams &kp)
 {
-	auto fn = merson_stage_tma2<STAGE, MODEL>;
+	auto fn = merson_stage_tma<STAGE, MODEL>;
 	static bool attr_set_dev[64] = {};        // the attribute is per device (and per template instance)
 	bool &attr_set = attr_set_dev[s->device & 63];
 	if (!attr_set) {
@@ -389,95 +405,98 @@ static cudaError_t launch_tma2_t(pft_solver *s, const TmaParams &kp)
 template <int STAGE>
 static cudaError_t launch_stage_tma_t(pft_solver *s, const TmaParams &kp)
 {
-	if (s->rows2) {
-		if (s->model == 2) return launch_tma2_t<STAGE, 2>(s, kp);
-		if (s->model == 0) return launch_tma2_t<STAGE, 0>(s, kp);
-		return launch_tma2_t<STAGE, 1>(s, kp);
-	}
-	if (s->share) {      // A/B variant, CTA barriers only
-		if (s->model == 2) return launch_tma_t<STAGE, 2, true, false>(s, kp);
-		if (s->model == 0) return launch_tma_t<STAGE, 0, true, false>(s, kp);
-		return launch_tma_t<STAGE, 1, true, false>(s, kp);
-	}
-	if (s->model == 2) return s->split ? launch_tma_t<STAGE, 2, false, true>(s, kp) : launch_tma_t<STAGE, 2, false, false>(s, kp);
-	if (s->model == 0) return s->split ? launch_tma_t<STAGE, 0, false, true>(s, kp) : launch_tma_t<STAGE, 0, false, false>(s, kp);
-	return s->split ? launch_tma_t<STAGE, 1, false, true>(s, kp) : launch_tma_t<STAGE, 1, false, false>(s, kp);
+	if (s->model == 2) return launch_tma_t<STAGE, 2>(s, kp);
+	if (s->model == 0) return launch_tma_t<STAGE, 0>(s, kp);
+	return launch_tma_t<STAGE, 1>(s, kp);
 }
 
-// peer path: where this launch pushes its boundary planes and whom it signals
-static void fill_peer_args(pft_solver *s, PeerArgs *pr, int out)
+// peer path: where a stage pushes its boundary planes and whom it signals
+static void fill_peer_args(pft_solver *s, PeerArgs *pr, int stage)
 {
 	const int r = s->cs.rank, R = s->cs.nranks;
 	const size_t plane_b = (size_t)s->g.plane * sizeof(double);
+	const int outs[5] = {A_K1, A_A3, A_K3, A_K4, -1};
 	pr->rank = r; pr->nranks = R;
 	pr->nzc = s->nzc;
-	pr->hseq = ++s->hseq;
 	pr->my_flags = ((SyncBlock *)s->slab)->halo_flag;
 	pr->tickets = s->halo_tickets;
 	pr->wait_lo = (r > 0); pr->wait_hi = (r < R - 1);
 	for (int q = 0; q < R; q++) pr->ranks[q] = (SyncBlock *)s->peer_base[q];
-	if (r > 0) {        // the lower neighbour's UPPER ghost plane (index n3'+1) and its halo_flag[1]
-		char *pb = s->peer_base[r - 1];
-		const size_t gp = (size_t)(s->peer_n3[r - 1] + 1) * plane_b;
-		pr->lo_p = (double *)(pb + s->off[out][1] + gp);
-		pr->lo_u = s->heat ? (double *)(pb + s->off[out][0] + gp) : nullptr;
-		pr->lo_flag = &((SyncBlock *)pb)->halo_flag[1];
+	for (int oi = 0; oi < 2; oi++) {
+		// stage 5 writes the candidate state pair: index [cur ^ 1], i.e. entry 0 = pair A_X, entry 1 = pair A_XN
+		const int out = (stage == 5) ? (oi == 0 ? A_X : A_XN) : outs[stage - 1];
+		if (r > 0) {        // the lower neighbour's UPPER ghost plane (index n3'+1) and its halo_flag[1]
+			char *pb = s->peer_base[r - 1];
+			const size_t gp = (size_t)(s->peer_n3[r - 1] + 1) * plane_b;
+			pr->lo_p[oi] = (double *)(pb + s->off[out][1] + gp);
+			pr->lo_u[oi] = s->heat ? (double *)(pb + s->off[out][0] + gp) : nullptr;
+			pr->lo_flag = &((SyncBlock *)pb)->halo_flag[1];
+		}
+		if (r < R - 1) {    // the upper neighbour's LOWER ghost plane (index 0) and its halo_flag[0]
+			char *pb = s->peer_base[r + 1];
+			pr->hi_p[oi] = (double *)(pb + s->off[out][1]);
+			pr->hi_u[oi] = s->heat ? (double *)(pb + s->off[out][0]) : nullptr;
+			pr->hi_flag = &((SyncBlock *)pb)->halo_flag[0];
+		}
 	}
-	if (r < R - 1) {    // the upper neighbour's LOWER ghost plane (index 0) and its halo_flag[0]
-		char *pb = s->peer_base[r + 1];
-		pr->hi_p = (double *)(pb + s->off[out][1]);
-		pr->hi_u = s->heat ? (double *)(pb + s->off[out][0]) : nullptr;
-		pr->hi_flag = &((SyncBlock *)pb)->halo_flag[0];
-	}
-#ifdef PFT_TRACE
-	// timing experiment only (wrong results): keep the flags, drop the plane pushes
-	static const int nopush = env_int("PFT_DEBUG_NOPUSH", 0);
-	if (nopush) pr->lo_p = pr->lo_u = pr->hi_p = pr->hi_u = nullptr;
-#endif
 }
 
-// stage launcher: fills the argument block for one Merson stage and (multi-GPU) exchanges the
-// z-boundary planes of what the stage produced
+// The argument blocks of the five stages.  Built once (and again when the transport changes):
+// nothing in them depends on the step length, the time level or the outcome of an attempt.
+static void build_params(pft_solver *s)
+{
+	const bool separate_nccl = s->cs.nranks > 1 && !s->p2p;
+	for (int stage = 1; stage <= 5; stage++) {
+		KParams &kp = s->kp[stage - 1];
+		kp.c = s->c;
+		kp.g = s->g;
+		StageArgs &a = kp.a;
+		memset(&a, 0, sizeof a);
+		a.ctl = s->ctl;
+		a.xu[0] = s->arr[A_X][0]; a.xp[0] = s->arr[A_X][1];
+		a.xu[1] = s->arr[A_XN][0]; a.xp[1] = s->arr[A_XN][1];
+		a.gl = s->gl;
+		a.k1u = s->arr[A_K1][0]; a.k1p = s->arr[A_K1][1];
+		a.k3u = s->arr[A_K3][0]; a.k3p = s->arr[A_K3][1];
+		a.k4u = s->arr[A_K4][0]; a.k4p = s->arr[A_K4][1];
+		a.au = s->arr[A_A3][0]; a.ap = s->arr[A_A3][1];
+		const int outs[5] = {A_K1, A_A3, A_K3, A_K4, A_XN};
+		a.ou = s->arr[outs[stage - 1]][0]; a.op = s->arr[outs[stage - 1]][1];
+		if (s->p2p) fill_peer_args(s, &a.pr, stage);
+		else a.pr.nzc = s->nzc;
+		a.pr.rank = s->cs.rank;
+		a.pr.nranks = s->p2p ? s->cs.nranks : 1;       // the in-kernel error-max exchange exists on the peer path only
+		if (stage == 5) {
+			a.slot = s->slot_dev;
+			a.tab = s->tab_dev;
+			a.nblocks = s->grid.x * s->grid.y * s->grid.z;
+			a.fin_mode = separate_nccl ? FIN_STORE_LOCAL : (s->dev_pow ? FIN_DECIDE : FIN_PUBLISH_EPS);
+		}
+		if (s->use_tma) {
+			TmaParams &tp = s->tp[stage - 1];
+			tp.c = kp.c; tp.g = kp.g; tp.a = kp.a;
+			tp.bx = s->bx; tp.by = s->by; tp.as = s->as;
+			// array order of a stage: p-type arrays, u-type arrays, gl (pft_kernels_tma.cuh, stage_np)
+			const int src[5][4] = {{A_X, -1, -1, -1}, {A_X, A_K1, -1, -1}, {A_A3, -1, -1, -1}, {A_X, A_K1, A_K3, -1}, {A_X, A_K1, A_K3, A_K4}};
+			const int np = stage_np(stage);
+			for (int m = 0; m < np; m++) {
+				tp.maps[m] = s->tmap[src[stage - 1][m]][1];
+				tp.maps[np + m] = s->tmap[src[stage - 1][m]][0];
+			}
+			tp.maps[2 * np] = s->tmap_gl;
+			tp.xalt[0] = s->tmap[A_XN][1];
+			tp.xalt[1] = s->tmap[A_XN][0];
+		}
+	}
+	s->params_ok = true;
+}
+
 static int exchange_pair(pft_solver *s, double *u, double *p);
 
-static int launch_stage(pft_solver *s, int stage, double t_stage, double ha, double hb,
-                        int xin, int out, const int *cond, const pft_system *sys, double h_abs, double eps_scale)
+// one stage launch.  standalone != nullptr: a single right-hand-side evaluation outside the time loop
+static int launch_stage(pft_solver *s, int stage, const double *standalone_dir = nullptr)
 {
-	KParams kp;
-	kp.c = s->c;
-	kp.g = s->g;
-	StageArgs &a = kp.a;
-	memset(&a, 0, sizeof a);
-	a.xu = s->arr[xin][0]; a.xp = s->arr[xin][1]; a.gl = s->gl;
-	a.k1u = s->arr[A_K1][0]; a.k1p = s->arr[A_K1][1];
-	a.k3u = s->arr[A_K3][0]; a.k3p = s->arr[A_K3][1];
-	a.k4u = s->arr[A_K4][0]; a.k4p = s->arr[A_K4][1];
-	a.au = s->arr[A_A3][0]; a.ap = s->arr[A_A3][1];
-	a.ou = s->arr[out][0]; a.op = s->arr[out][1];
-	a.ha = ha; a.hb = hb;
-	a.dir_u = dirichlet(s, t_stage);
-	a.cond = cond;
-	if (s->p2p) fill_peer_args(s, &a.pr, out);
-	if (stage == 5) {
-		a.delta = sys->delta; a.h_abs = h_abs; a.h_min = sys->h_min;
-		a.eps_scale = eps_scale; a.scale_eps = sys->delta_local ? 1 : 0;
-		a.handle_nan = sys->handle_nan;
-		a.ctl = s->ctl; a.slot = s->slot_dev; a.seq = ++s->seq;
-		a.nblocks = s->grid.x * s->grid.y * s->grid.z;
-	}
-#ifdef PFT_TRACE
-	if (!s->trace) {
-		if (cudaMalloc(&s->trace, sizeof(unsigned long long) * TRACE_CAP * TRACE_REC) != cudaSuccess) return fail(PFT_ENOMEM, "trace buffer");
-		cudaMemsetAsync(s->trace, 0, sizeof(unsigned long long) * TRACE_CAP * TRACE_REC, s->stream);
-	}
-	if (!s->trace_cta) {
-		if (cudaMalloc(&s->trace_cta, sizeof(unsigned long long) * TRACE_CTA_LAUNCHES * 4096) != cudaSuccess) return fail(PFT_ENOMEM, "trace buffer");
-		cudaMemsetAsync(s->trace_cta, 0, sizeof(unsigned long long) * TRACE_CTA_LAUNCHES * 4096, s->stream);
-	}
-	a.trace = ((int)s->trace_stage.size() < TRACE_CAP) ? s->trace + s->trace_stage.size() * TRACE_REC : nullptr;
-	a.trace_cta = ((int)s->trace_stage.size() < TRACE_CTA_LAUNCHES) ? s->trace_cta + s->trace_stage.size() * 4096 : nullptr;
-	if (a.trace) s->trace_stage.push_back(stage);
-#endif
+	if (!s->params_ok) build_params(s);
 	StageTimer tm{};
 	if (s->profile) {
 		cudaEventCreate(&tm.a); cudaEventCreate(&tm.b); tm.stage = stage;
@@ -485,40 +504,44 @@ static int launch_stage(pft_solver *s, int stage, double t_stage, double ha, dou
 	}
 	cudaError_t e;
 	if (s->use_tma) {
-		TmaParams tp;
-		tp.c = kp.c; tp.g = kp.g; tp.a = kp.a;
-		tp.bx = s->bx; tp.by = s->by; tp.as = s->as;
-		// array order of a stage: p-type arrays, u-type arrays, gl (pft_kernels_tma.cuh, stage_np)
-		const int src[5][4] = {{xin, -1, -1, -1}, {xin, A_K1, -1, -1}, {A_A3, -1, -1, -1}, {xin, A_K1, A_K3, -1}, {xin, A_K1, A_K3, A_K4}};
-		const int np = stage_np(stage);
-		for (int m = 0; m < np; m++) {
-			tp.maps[m] = s->tmap[src[stage - 1][m]][1];
-			tp.maps[np + m] = s->tmap[src[stage - 1][m]][0];
+		const TmaParams *tp = &s->tp[stage - 1];
+		TmaParams alone;
+		if (standalone_dir) {
+			alone = *tp;
+			memset(&alone.a.pr, 0, sizeof alone.a.pr);
+			alone.a.pr.nzc = s->nzc; alone.a.pr.nranks = 1;
+			alone.a.standalone = 1; alone.a.standalone_cur = s->cur; alone.a.dir_standalone = *standalone_dir;
+			tp = &alone;
 		}
-		tp.maps[2 * np] = s->tmap_gl;
 		switch (stage) {
-		case 1: e = launch_stage_tma_t<1>(s, tp); break;
-		case 2: e = launch_stage_tma_t<2>(s, tp); break;
-		case 3: e = launch_stage_tma_t<3>(s, tp); break;
-		case 4: e = launch_stage_tma_t<4>(s, tp); break;
-		default: e = launch_stage_tma_t<5>(s, tp); break;
+		case 1: e = launch_stage_tma_t<1>(s, *tp); break;
+		case 2: e = launch_stage_tma_t<2>(s, *tp); break;
+		case 3: e = launch_stage_tma_t<3>(s, *tp); break;
+		case 4: e = launch_stage_tma_t<4>(s, *tp); break;
+		default: e = launch_stage_tma_t<5>(s, *tp); break;
 		}
-	} else
-	switch (stage) {
-	case 1: e = launch_stage_t<1>(s, kp); break;
-	case 2: e = launch_stage_t<2>(s, kp); break;
-	case 3: e = launch_stage_t<3>(s, kp); break;
-	case 4: e = launch_stage_t<4>(s, kp); break;
-	default: e = launch_stage_t<5>(s, kp); break;
+	} else {
+		const KParams *kp = &s->kp[stage - 1];
+		KParams alone;
+		if (standalone_dir) {
+			alone = *kp;
+			memset(&alone.a.pr, 0, sizeof alone.a.pr);
+			alone.a.pr.nzc = s->nzc; alone.a.pr.nranks = 1;
+			alone.a.standalone = 1; alone.a.standalone_cur = s->cur; alone.a.dir_standalone = *standalone_dir;
+			kp = &alone;
+		}
+		switch (stage) {
+		case 1: e = launch_stage_t<1>(s, *kp); break;
+		case 2: e = launch_stage_t<2>(s, *kp); break;
+		case 3: e = launch_stage_t<3>(s, *kp); break;
+		case 4: e = launch_stage_t<4>(s, *kp); break;
+		default: e = launch_stage_t<5>(s, *kp); break;
+		}
 	}
 	if (e != cudaSuccess) return fail(PFT_ECUDA, "stage %d launch: %s", stage, cudaGetErrorString(e));
 	if (s->profile) { cudaEventRecord(tm.b, s->stream); s->timers.push_back(tm); }
 	s->st.kernel_launches++;
 	s->st.stage_launches[stage - 1]++;
-	if (s->cs.nranks > 1 && !s->p2p) {
-		int rc = exchange_pair(s, s->heat ? s->arr[out][0] : nullptr, s->arr[out][1]);
-		if (rc) return rc;
-	}
 	return 0;
 }
 
@@ -541,6 +564,7 @@ static void drain_timers(pft_solver *s)
 static int exchange_pair(pft_solver *s, double *u, double *p)
 {
 	if (s->cs.nranks <= 1) return 0;
+	if (s->group) return fail(PFT_ESTATE, "members of an in-process group exchange their boundary planes through pft_group_upload");
 	if (!s->have_comm) return fail(PFT_ESTATE, "nranks > 1 but pft_comm_init was not called");
 	const size_t n = (size_t)s->g.plane;
 	const int r = s->cs.rank, R = s->cs.nranks, n3 = s->g.n3;
@@ -579,10 +603,10 @@ static int slab_n3(int total_n3, int nranks, int r)
 	return total_n3 / nranks + (r < total_n3 % nranks ? 1 : 0);
 }
 
-// Peer path: every rank exports its slab with CUDA IPC, the handles travel once through the NCCL
-// communicator, and from then on the time loop contains no collective call at all: boundary planes
-// are stored straight into the neighbours' ghost planes by the stage kernels, flags and the
-// per-slab error maxima travel as peer stores (pft_kernels.cuh, "peer-memory halo exchange").
+// Peer path between processes: every rank exports its slab with CUDA IPC, the handles travel once
+// through the NCCL communicator, and from then on the time loop contains no collective call at all:
+// boundary planes are stored straight into the neighbours' ghost planes by the stage kernels, flags
+// and the per-slab error maxima travel as peer stores (pft_kernels.cuh, "peer-memory halo exchange").
 static int setup_p2p(pft_solver *s)
 {
 	const int R = s->cs.nranks, r = s->cs.rank;
@@ -626,12 +650,12 @@ static int setup_p2p(pft_solver *s)
 	CU(cudaStreamSynchronize(s->stream));
 	cudaFree(df);
 	s->p2p = (flag == 1.0);
+	s->ipc = s->p2p;
 	if (!s->p2p)
 		for (int q = 0; q < R; q++) {
 			if (s->peer_base[q] && s->peer_base[q] != s->slab) cudaIpcCloseMemHandle(s->peer_base[q]);
 			s->peer_base[q] = nullptr;
 		}
-	s->speculate = s->speculate_req && (s->cs.nranks == 1 || s->p2p);
 	return 0;
 }
 
@@ -639,6 +663,7 @@ extern "C" int pft_comm_init(pft_solver *s, const void *id128)
 {
 	if (!s || !id128) return fail(PFT_EINVAL, "null argument");
 	if (s->cs.nranks <= 1) return 0;
+	if (s->group) return fail(PFT_ESTATE, "this solver belongs to an in-process group");
 	int rc = nccl_load();
 	if (rc) return rc;
 	CU(cudaSetDevice(s->device));
@@ -651,6 +676,7 @@ extern "C" int pft_comm_init(pft_solver *s, const void *id128)
 		rc = setup_p2p(s);
 		if (rc) return rc;
 	}
+	s->params_ok = false;
 	return 0;
 }
 
@@ -694,13 +720,9 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	s->device = device;
 	s->model = (cs->calc_mode == 2) ? 2 : (cs->calc_mode % 10);
 	s->heat = !(cs->calc_mode == 10 || cs->calc_mode == 11);
-	// Sharing face fluxes through shared memory saves ~25% of the fp64 work but costs a second CTA
-	// barrier per plane; measured on B200 it loses (profiles/round1_tuning.md), so it is opt-in.
-	s->share = s->heat && !(flags & PFT_FLAG_NO_FLUX_SHARING) && ((flags & PFT_FLAG_FLUX_SHARING) || env_int("PFT_SHARE", 0));
-	s->speculate_req = !(flags & PFT_FLAG_NO_SPECULATION) && !env_int("PFT_NO_SPECULATION", 0);
-	s->speculate = s->speculate_req && cs->nranks == 1;      // N > 1: enabled by the peer path (setup_p2p)
 	s->profile = env_int("PFT_PROFILE_STAGES", 0) != 0;
 	s->pdl = !s->profile && env_int("PFT_NO_PDL", 0) == 0;
+	s->depth = (flags & PFT_FLAG_NO_RUNAHEAD) ? 1 : std::max(1, std::min(64, env_int("PFT_RUNAHEAD", 6)));
 	make_consts(s);
 
 	Geom &g = s->g;
@@ -716,39 +738,34 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	s->padded = (long long)PFT_NVAR * s->N1 * s->N2 * s->N3;
 
 	s->use_tma = s->heat && !(flags & PFT_FLAG_LEGACY_LOADS) && !env_int("PFT_LEGACY", 0);
-	s->rows2 = s->use_tma && !s->share && env_int("PFT_ROWS2", 0) != 0;    // measured slower than one cell per thread (profiles/round1_tuning.md)
-	const int rpt = s->rows2 ? 2 : 1;        // cell rows per thread
-	int max_threads = env_int("PFT_THREADS", s->rows2 ? 160 : 256);     // two or three CTAs per SM overlap each other's barrier waits
+	int max_threads = env_int("PFT_THREADS", 256);     // two or three CTAs per SM overlap each other's barrier waits
 	if (max_threads < 32) max_threads = 32;
 	if (max_threads > 512) max_threads = 512;
 	if (s->use_tma && max_threads > 256) max_threads = 256;      // __launch_bounds__ of the TMA kernels
-	choose_tile(cs->n1, (cs->n2 + rpt - 1) / rpt, max_threads, &s->TX, &s->TY);
+	choose_tile(cs->n1, cs->n2, max_threads, &s->TX, &s->TY);
 	if (env_int("PFT_TX", 0) > 0) s->TX = env_int("PFT_TX", 0);
 	if (env_int("PFT_TY", 0) > 0) s->TY = env_int("PFT_TY", 0);
 	if (s->TX & 1) s->TX++;                  // tile origins must be even (TMA inner-offset alignment)
-	if (s->TX * s->TY > (s->use_tma ? 256 : 512) || rpt * s->TX * s->TY < 2 * s->TX + 2 * rpt * s->TY) {
+	if (s->TX * s->TY > (s->use_tma ? 256 : 512) || s->TX * s->TY < 2 * s->TX + 2 * s->TY) {
 		int tx_ = s->TX, ty_ = s->TY;
 		delete s;
 		return fail(PFT_EINVAL, "tile %dx%d unusable (needs TX*TY <= 512 and enough threads for the halo ring)", tx_, ty_);
 	}
-	const int tile_rows = rpt * s->TY;
-	int tiles_xy = ((cs->n1 + s->TX - 1) / s->TX) * ((cs->n2 + tile_rows - 1) / tile_rows);
+	int tiles_xy = ((cs->n1 + s->TX - 1) / s->TX) * ((cs->n2 + s->TY - 1) / s->TY);
 	s->nzc = choose_chunks(tiles_xy, cs->n3, prop.multiProcessorCount);
 	if (env_int("PFT_ZCHUNKS", 0) > 0) s->nzc = std::min(cs->n3, env_int("PFT_ZCHUNKS", 0));
 	g.zc = (cs->n3 + s->nzc - 1) / s->nzc;
 	s->nzc = (cs->n3 + g.zc - 1) / g.zc;
-	s->grid = dim3((cs->n1 + s->TX - 1) / s->TX, (cs->n2 + tile_rows - 1) / tile_rows, s->nzc);
+	s->grid = dim3((cs->n1 + s->TX - 1) / s->TX, (cs->n2 + s->TY - 1) / s->TY, s->nzc);
 	s->block = dim3(s->TX, s->TY, 1);
 	{
 		int NF = s->heat ? 3 : 1;
 		size_t ts = (size_t)(s->TX + 2) * (s->TY + 2);
-		size_t fl = s->share ? (size_t)s->TY * (s->TX + 1) + (size_t)(s->TY + 1) * s->TX : 0;
-		s->smem = (2 * NF * ts + fl) * sizeof(double);
+		s->smem = (2 * NF * ts) * sizeof(double);
 	}
 
 	CUS(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-	CUS(cudaEventCreate(&s->ev0)); CU(cudaEventCreate(&s->ev1));
-	CUS(cudaEventCreateWithFlags(&s->ev_red, cudaEventDisableTiming));
+	CUS(cudaEventCreate(&s->ev0)); CUS(cudaEventCreate(&s->ev1));
 	const size_t fb = ((size_t)s->field * sizeof(double) + 255) & ~(size_t)255;
 	{
 		// layout: identical on every rank of a run with equal slab depth; offsets are exchanged anyway
@@ -773,17 +790,15 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	CUS(cudaMalloc(&s->halo_tickets, 2 * sizeof(unsigned int)));
 	CUS(cudaMemsetAsync(s->halo_tickets, 0, 2 * sizeof(unsigned int), s->stream));
 
-	s->split = s->use_tma && !s->share && env_int("PFT_SPLIT", 0) != 0;
 	if (s->use_tma) {
 		s->bx = s->TX + 4;                   // box starts at x = i0-2 (16-byte aligned inner offset), TX is even
-		s->by = (s->rows2 ? 2 : 1) * s->TY + 2;
+		s->by = s->TY + 2;
 		s->as = (s->bx * s->by + 15) & ~15;  // each array buffer starts 128-byte aligned
-		size_t fl = s->share ? (size_t)s->TY * (s->TX + 1) + (size_t)(s->TY + 1) * s->TX : 0;
 		size_t worst = 0;
 		for (int st = 1; st <= 5; st++) {
 			int na = 2 * stage_np(st) + 1;
 			bool form = !(st == 1 || st == 3);
-			s->smem_tma[st - 1] = ((size_t)TMA_STAGES * na * s->as + (form ? (s->split && !s->rows2 ? 6 : 4) * (size_t)s->as : 0) + fl) * sizeof(double);
+			s->smem_tma[st - 1] = ((size_t)TMA_STAGES * na * s->as + (form ? 4 * (size_t)s->as : 0)) * sizeof(double);
 			worst = std::max(worst, s->smem_tma[st - 1]);
 		}
 		if (worst > 225 * 1024) { pft_destroy(s); return fail(PFT_EINVAL, "tile %dx%d needs %zu bytes of shared memory", s->TX, s->TY, worst); }
@@ -795,19 +810,29 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 		int rc = make_tensor_map(s, &s->tmap_gl, s->gl);
 		if (rc) { pft_destroy(s); return rc; }
 	}
-	CUS(cudaMalloc(&s->ctl, sizeof(Ctl)));
-	CUS(cudaMemsetAsync(s->ctl, 0, sizeof(Ctl), s->stream));
-	CUS(cudaMalloc(&s->red, 2 * sizeof(double)));
-	CUS(cudaHostAlloc(&s->red_host, 2 * sizeof(double), cudaHostAllocDefault));
+	CUS(cudaMalloc(&s->ctl, sizeof(StepCtl)));
+	CUS(cudaMemsetAsync(s->ctl, 0, sizeof(StepCtl), s->stream));
+	CUS(cudaHostAlloc(&s->ctl_host, sizeof(StepCtl), cudaHostAllocDefault));
 	CUS(cudaHostAlloc(&s->slot, sizeof(HostSlot), cudaHostAllocMapped));
 	memset(s->slot, 0, sizeof(HostSlot));
 	CUS(cudaHostGetDevicePointer(&s->slot_dev, s->slot, 0));
+	{
+		const PowGate &pg = pow_gate();
+		s->dev_pow = pg.usable && !(flags & PFT_FLAG_HOST_POW);
+		if (pg.usable) {     // (the tables are uploaded even with PFT_FLAG_HOST_POW: pft_debug_pow checks the device twin)
+			CUS(cudaMalloc(&s->tab_dev, sizeof(PowTables)));
+			CUS(cudaMemcpyAsync(s->tab_dev, &pg.tab, sizeof(PowTables), cudaMemcpyHostToDevice, s->stream));
+		} else if (env_int("PFT_VERBOSE", 0))
+			fprintf(stderr, "pft_b200: device step-size controller off, the host supplies pow() per attempt: %s\n", pg.why);
+	}
 	CUS(cudaStreamSynchronize(s->stream));
 
 	memset(&s->st, 0, sizeof s->st);
 	s->st.tile_x = s->TX; s->st.tile_y = s->TY; s->st.z_chunk = g.zc; s->st.threads = s->TX * s->TY;
 	s->st.grid_blocks = s->grid.x * s->grid.y * s->grid.z;
 	s->st.bytes_per_field = (long)fb;
+	s->st.device_pow = s->dev_pow ? 1 : 0;
+	s->st.runahead = s->depth;
 	*out = s;
 	return 0;
 }
@@ -819,20 +844,18 @@ extern "C" int pft_destroy(pft_solver *s)
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	drain_timers(s);
 	if (s->have_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
-	for (int r = 0; r < PFT_MAX_RANKS; r++)
-		if (s->peer_base[r] && s->peer_base[r] != s->slab) cudaIpcCloseMemHandle(s->peer_base[r]);
+	if (s->ipc)
+		for (int r = 0; r < PFT_MAX_RANKS; r++)
+			if (s->peer_base[r] && s->peer_base[r] != s->slab) cudaIpcCloseMemHandle(s->peer_base[r]);
 	if (s->slab) cudaFree(s->slab);
 	if (s->halo_tickets) cudaFree(s->halo_tickets);
-	if (s->trace) cudaFree(s->trace);
-	if (s->trace_cta) cudaFree(s->trace_cta);
 	if (s->stage_buf) cudaFree(s->stage_buf);
 	if (s->ctl) cudaFree(s->ctl);
-	if (s->red) cudaFree(s->red);
-	if (s->red_host) cudaFreeHost(s->red_host);
+	if (s->tab_dev) cudaFree(s->tab_dev);
+	if (s->ctl_host) cudaFreeHost(s->ctl_host);
 	if (s->slot) cudaFreeHost(s->slot);
 	if (s->ev0) cudaEventDestroy(s->ev0);
 	if (s->ev1) cudaEventDestroy(s->ev1);
-	if (s->ev_red) cudaEventDestroy(s->ev_red);
 	if (s->stream) cudaStreamDestroy(s->stream);
 	delete s;
 	return 0;
@@ -850,58 +873,116 @@ static int ensure_stage(pft_solver *s)
 	return 0;
 }
 
-static void repack(pft_solver *s, double *padded_var, double *compact, int dir)
+// planes klo .. khi-1 (klo = -1 / khi = n3+1 reach into the z-ghost planes of both layouts)
+static void repack(pft_solver *s, double *padded_var, double *compact, int dir, int klo, int khi)
 {
 	const Geom &g = s->g;
-	long long total = (long long)g.n1 * g.n2 * g.n3;
+	long long total = (long long)g.n1 * g.n2 * (khi - klo);
 	int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-	PFT_LAUNCH(repack_kernel, dim3(blocks), dim3(256), 0, s->stream, padded_var, compact, g.n1, g.n2, g.n3, g.px, g.plane,
+	PFT_LAUNCH(repack_kernel, dim3(blocks), dim3(256), 0, s->stream, padded_var, compact, g.n1, g.n2, klo, khi, g.px, g.plane,
 	           s->N1, (long long)s->N1 * s->N2, PFT_BT, dir);
 	s->st.kernel_launches++;
 }
 
-static int refresh_halos(pft_solver *s)
+static int refresh_halos(pft_solver *s, unsigned mask)
 {
-	if (s->cs.nranks <= 1) return 0;
-	int rc = exchange_pair(s, s->arr[A_X][0], s->arr[A_X][1]);
-	if (rc) return rc;
-	return exchange_pair(s, s->gl, nullptr);
+	if (s->cs.nranks <= 1 || s->group) return 0;
+	int rc = 0;
+	if (mask & (PFT_FIELD_U | PFT_FIELD_P))
+		rc = exchange_pair(s, (mask & PFT_FIELD_U) ? s->arr[s->cur ? A_XN : A_X][0] : nullptr, (mask & PFT_FIELD_P) ? s->arr[s->cur ? A_XN : A_X][1] : nullptr);
+	if (!rc && (mask & PFT_FIELD_GL)) rc = exchange_pair(s, s->gl, nullptr);
+	return rc;
 }
 
-extern "C" int pft_upload(pft_solver *s, const double *x)
+static double *field_ptr(pft_solver *s, int q)
+{
+	return q == 2 ? s->gl : s->arr[s->cur ? A_XN : A_X][q];
+}
+
+// One variable of a padded host array -> device.  `host_var` points at padded plane 0 of that variable as this
+// slab sees it; lo / hi: also take the plane below / above the slab (a neighbouring slab's boundary rows of the
+// SAME host array: in-process groups) into the z-ghost plane.  Only the planes that are used travel.
+static int upload_var(pft_solver *s, const double *host_var, int q, int lo, int hi)
+{
+	const long long rowsize = (long long)s->N1 * s->N2, SIZE = s->padded / PFT_NVAR;
+	const long long p0 = PFT_BT - lo, np = s->g.n3 + lo + hi;
+	double *st = s->stage_buf + q * SIZE;
+	CU(cudaMemcpyAsync(st + p0 * rowsize, host_var + p0 * rowsize, (size_t)(np * rowsize) * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+	repack(s, st, field_ptr(s, q), 0, -lo, s->g.n3 + hi);
+	s->stage_shell[q] = true;
+	return 0;
+}
+
+// device -> the interior nodes of one variable of a padded host array.  The x/y ghost nodes inside the copied
+// planes come from the staging image: the ones of the caller's last upload of that variable if there was one
+// (one-shot), otherwise they are fetched from the host array first, so that ghost nodes are never altered.
+static int download_var(pft_solver *s, double *host_var, int q)
+{
+	const long long rowsize = (long long)s->N1 * s->N2, SIZE = s->padded / PFT_NVAR;
+	const long long p0 = PFT_BT, np = s->g.n3;
+	double *st = s->stage_buf + q * SIZE;
+	if (!s->stage_shell[q])
+		CU(cudaMemcpyAsync(st + p0 * rowsize, host_var + p0 * rowsize, (size_t)(np * rowsize) * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+	repack(s, st, field_ptr(s, q), 1, 0, s->g.n3);
+	CU(cudaMemcpyAsync(host_var + p0 * rowsize, st + p0 * rowsize, (size_t)(np * rowsize) * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+	s->stage_shell[q] = false;
+	return 0;
+}
+
+extern "C" int pft_upload_fields(pft_solver *s, const double *x, unsigned mask)
 {
 	if (!s || !x) return fail(PFT_EINVAL, "null argument");
+	if (s->group) return fail(PFT_ESTATE, "members of an in-process group are filled through pft_group_upload");
 	CU(cudaSetDevice(s->device));
 	int rc = ensure_stage(s);
 	if (rc) return rc;
 	const long long SIZE = s->padded / PFT_NVAR;
-	CU(cudaMemcpyAsync(s->stage_buf, x, (size_t)s->padded * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-	repack(s, s->stage_buf, s->arr[A_X][0], 0);
-	repack(s, s->stage_buf + SIZE, s->arr[A_X][1], 0);
-	repack(s, s->stage_buf + 2 * SIZE, s->gl, 0);
+	for (int q = 0; q < PFT_NVAR; q++)
+		if ((mask >> q) & 1u)
+			if ((rc = upload_var(s, x + q * SIZE, q, 0, 0))) return rc;
 	CU(cudaGetLastError());
-	rc = refresh_halos(s);
+	rc = refresh_halos(s, mask);
 	if (rc) return rc;
 	CU(cudaStreamSynchronize(s->stream));
 	s->k1_valid = false;
 	return 0;
 }
 
-extern "C" int pft_download(pft_solver *s, double *x)
+extern "C" int pft_download_fields(pft_solver *s, double *x, unsigned mask)
 {
 	if (!s || !x) return fail(PFT_EINVAL, "null argument");
 	CU(cudaSetDevice(s->device));
 	int rc = ensure_stage(s);
 	if (rc) return rc;
 	const long long SIZE = s->padded / PFT_NVAR;
-	// the staging image still holds the ghost shell of the last upload (or of this host array)
-	CU(cudaMemcpyAsync(s->stage_buf, x, (size_t)s->padded * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-	repack(s, s->stage_buf, s->arr[A_X][0], 1);
-	repack(s, s->stage_buf + SIZE, s->arr[A_X][1], 1);
-	repack(s, s->stage_buf + 2 * SIZE, s->gl, 1);
+	for (int q = 0; q < PFT_NVAR; q++)
+		if ((mask >> q) & 1u)
+			if ((rc = download_var(s, x + q * SIZE, q))) return rc;
 	CU(cudaGetLastError());
-	CU(cudaMemcpyAsync(x, s->stage_buf, (size_t)s->padded * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
 	CU(cudaStreamSynchronize(s->stream));
+	return 0;
+}
+
+extern "C" int pft_upload(pft_solver *s, const double *x) { return pft_upload_fields(s, x, PFT_FIELD_ALL); }
+extern "C" int pft_download(pft_solver *s, double *x) { return pft_download_fields(s, x, PFT_FIELD_ALL); }
+
+extern "C" int pft_host_register(void *ptr, unsigned long long bytes)
+{
+	if (!ptr || !bytes) return fail(PFT_EINVAL, "null argument");
+#ifndef PFT_CUDA_EMU
+	cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+	if (e != cudaSuccess) { cudaGetLastError(); return fail(PFT_ECUDA, "cudaHostRegister(%llu bytes): %s", bytes, cudaGetErrorString(e)); }
+#endif
+	return 0;
+}
+
+extern "C" int pft_host_unregister(void *ptr)
+{
+	if (!ptr) return fail(PFT_EINVAL, "null argument");
+#ifndef PFT_CUDA_EMU
+	cudaError_t e = cudaHostUnregister(ptr);
+	if (e != cudaSuccess) { cudaGetLastError(); return fail(PFT_ECUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+#endif
 	return 0;
 }
 
@@ -911,6 +992,7 @@ static int dense_io(pft_solver *s, double *host, double *compact, int dir)
 	long long total = (long long)g.n1 * g.n2 * g.n3;
 	int rc = ensure_stage(s);
 	if (rc) return rc;
+	s->stage_shell[0] = false;      // the dense image goes through the head of the staging buffer
 	int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
 	if (dir == 0) {
 		CU(cudaMemcpyAsync(s->stage_buf, host, (size_t)total * sizeof(double), cudaMemcpyHostToDevice, s->stream));
@@ -930,10 +1012,10 @@ extern "C" int pft_upload_interior(pft_solver *s, const double *u, const double 
 	if (!s) return fail(PFT_EINVAL, "null solver");
 	CU(cudaSetDevice(s->device));
 	int rc;
-	if (u && (rc = dense_io(s, const_cast<double *>(u), s->arr[A_X][0], 0))) return rc;
-	if (p && (rc = dense_io(s, const_cast<double *>(p), s->arr[A_X][1], 0))) return rc;
+	if (u && (rc = dense_io(s, const_cast<double *>(u), field_ptr(s, 0), 0))) return rc;
+	if (p && (rc = dense_io(s, const_cast<double *>(p), field_ptr(s, 1), 0))) return rc;
 	if (gl && (rc = dense_io(s, const_cast<double *>(gl), s->gl, 0))) return rc;
-	rc = refresh_halos(s);
+	rc = refresh_halos(s, (u ? PFT_FIELD_U : 0u) | (p ? PFT_FIELD_P : 0u) | (gl ? PFT_FIELD_GL : 0u));
 	if (rc) return rc;
 	CU(cudaStreamSynchronize(s->stream));
 	s->k1_valid = false;
@@ -945,58 +1027,44 @@ extern "C" int pft_download_interior(pft_solver *s, double *u, double *p, double
 	if (!s) return fail(PFT_EINVAL, "null solver");
 	CU(cudaSetDevice(s->device));
 	int rc;
-	if (u && (rc = dense_io(s, u, s->arr[A_X][0], 1))) return rc;
-	if (p && (rc = dense_io(s, p, s->arr[A_X][1], 1))) return rc;
+	if (u && (rc = dense_io(s, u, field_ptr(s, 0), 1))) return rc;
+	if (p && (rc = dense_io(s, p, field_ptr(s, 1), 1))) return rc;
 	if (gl && (rc = dense_io(s, gl, s->gl, 1))) return rc;
 	return 0;
 }
 
+// which: 0 x, 1 K1, 2 aux3, 3 K3, 4 K4, 5 x_new (the candidate of the last attempt)
 extern "C" int pft_debug_fetch(pft_solver *s, int which, double *u, double *p)
 {
 	if (!s || which < 0 || which >= A_COUNT) return fail(PFT_EINVAL, "bad array id %d", which);
 	CU(cudaSetDevice(s->device));
+	int pair = which;
+	if (which == A_X) pair = s->cur ? A_XN : A_X;
+	if (which == A_XN) pair = s->cur ? A_X : A_XN;
 	int rc;
 	if (u) {
-		if (s->arr[which][0]) { if ((rc = dense_io(s, u, s->arr[which][0], 1))) return rc; }
+		if (s->arr[pair][0]) { if ((rc = dense_io(s, u, s->arr[pair][0], 1))) return rc; }
 		else memset(u, 0, sizeof(double) * (size_t)s->g.n1 * s->g.n2 * s->g.n3);     // K_u == 0 in calc_mode 10/11
 	}
-	if (p && (rc = dense_io(s, p, s->arr[which][1], 1))) return rc;
+	if (p && (rc = dense_io(s, p, s->arr[pair][1], 1))) return rc;
 	return 0;
 }
 
-extern "C" int pft_debug_trace(pft_solver *s, unsigned long long *records, int *stages, int max_records)
+extern "C" int pft_debug_pow(pft_solver *s, const double *x, double y, double *out, int n)
 {
-	if (!s || !records || !stages) return fail(PFT_EINVAL, "null argument");
-#ifdef PFT_TRACE
+	if (!s || !x || !out || n < 0) return fail(PFT_EINVAL, "bad argument");
+	if (!s->tab_dev) return fail(PFT_ESTATE, "the pow tables of the host C library are not available: %s", pow_gate().why);
 	CU(cudaSetDevice(s->device));
+	double *d = nullptr;
+	CU(cudaMalloc(&d, sizeof(double) * 2 * (size_t)std::max(n, 1)));
+	CU(cudaMemcpyAsync(d, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+	PFT_LAUNCH(pow_twin_kernel, dim3(148 * 4), dim3(256), 0, s->stream, s->tab_dev, d, y, d + n, n);
+	s->st.kernel_launches++;
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(out, d + n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
 	CU(cudaStreamSynchronize(s->stream));
-	const int n = std::min((int)s->trace_stage.size(), max_records);
-	if (n > 0) CU(cudaMemcpy(records, s->trace, sizeof(unsigned long long) * TRACE_REC * n, cudaMemcpyDeviceToHost));
-	for (int q = 0; q < n; q++) stages[q] = s->trace_stage[q];
-	s->trace_stage.clear();
-	if (s->trace) CU(cudaMemset(s->trace, 0, sizeof(unsigned long long) * TRACE_CAP * TRACE_REC));
-	return n;
-#else
-	(void)max_records;
-	return fail(PFT_EINVAL, "this library was built without -DPFT_TRACE (make libpft_b200_trace.so)");
-#endif
-}
-
-extern "C" int pft_debug_trace_cta(pft_solver *s, unsigned long long *out, int launches)
-{
-	if (!s || !out) return fail(PFT_EINVAL, "null argument");
-#ifdef PFT_TRACE
-	CU(cudaSetDevice(s->device));
-	CU(cudaStreamSynchronize(s->stream));
-	const int n = std::min(launches, TRACE_CTA_LAUNCHES);
-	if (!s->trace_cta) return 0;
-	CU(cudaMemcpy(out, s->trace_cta, sizeof(unsigned long long) * 4096 * n, cudaMemcpyDeviceToHost));
-	CU(cudaMemset(s->trace_cta, 0, sizeof(unsigned long long) * TRACE_CTA_LAUNCHES * 4096));
-	return n;
-#else
-	(void)launches;
-	return fail(PFT_EINVAL, "this library was built without -DPFT_TRACE (make libpft_b200_trace.so)");
-#endif
+	cudaFree(d);
+	return 0;
 }
 
 extern "C" int pft_rasterise(pft_solver *s, const double *xyz_raw, int count)
@@ -1005,27 +1073,75 @@ extern "C" int pft_rasterise(pft_solver *s, const double *xyz_raw, int count)
 	if (count == 0) return 0;
 	CU(cudaSetDevice(s->device));
 	const pft_case &cs = s->cs;
-	std::vector<double> b(3 * (size_t)count);
-	for (int q = 0; q < count; q++) {   // equation.c:480-482
-		b[q] = xyz_raw[3 * q] * cs.param[P_beads_scaling] + cs.param[P_beads_offset_x];
-		b[count + q] = xyz_raw[3 * q + 1] * cs.param[P_beads_scaling] + cs.param[P_beads_offset_y];
-		b[2 * (size_t)count + q] = xyz_raw[3 * q + 2] * cs.param[P_beads_scaling] + cs.param[P_beads_offset_z];
-	}
-	double *d = nullptr;
-	CU(cudaMalloc(&d, b.size() * sizeof(double)));
-	CU(cudaMemcpyAsync(d, b.data(), b.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
 	const Geom &g = s->g;
+	// centres in grid coordinates (equation.c:480-482), sorted into uniform bins of the culling radius:
+	// a node only visits the 27 bins around it.  Bit-identical to testing every sphere: a sphere that is
+	// skipped lies further away than R + 19.5/s, where its profile is exactly 0 (see rasterise_kernel).
+	std::vector<double> b(3 * (size_t)count);
+	for (int q = 0; q < count; q++) {
+		b[3 * (size_t)q] = xyz_raw[3 * q] * cs.param[P_beads_scaling] + cs.param[P_beads_offset_x];
+		b[3 * (size_t)q + 1] = xyz_raw[3 * q + 1] * cs.param[P_beads_scaling] + cs.param[P_beads_offset_y];
+		b[3 * (size_t)q + 2] = xyz_raw[3 * q + 2] * cs.param[P_beads_scaling] + cs.param[P_beads_offset_z];
+	}
+	const double sfac = 0.5 / cs.param[P_xi_gl];
+	const double cut = cs.param[P_ball_radius] + 19.5 / sfac;
+	RasterBins rb;
+	double lo[3] = {0.0, 0.0, cs.L3 * (0.5 + cs.first_row) / cs.total_n3}, hi[3] = {cs.L1, cs.L2, cs.L3 * (0.5 + cs.first_row + g.n3 - 1) / cs.total_n3};
+	// bin edge >= cut; at most 64 bins per direction
+	for (int d = 0; d < 3; d++) {
+		rb.org[d] = lo[d];
+		const double ext = std::max(hi[d] - lo[d], 1e-300);
+		int nb = (int)std::min(64.0, std::max(1.0, floor(ext / cut)));
+		if (env_int("PFT_RASTER_ONE_BIN", 0)) nb = 1;      // A/B and test: every node tests every sphere
+		rb.nb[d] = nb;
+		rb.inv[d] = nb / ext;
+	}
+	const int nbins = rb.nb[0] * rb.nb[1] * rb.nb[2];
+	auto bin_of = [&](const double *c, int d) {
+		double f = (c[d] - rb.org[d]) * rb.inv[d];
+		int i = (f < 0) ? 0 : (f >= rb.nb[d] ? rb.nb[d] - 1 : (int)f);      // spheres outside the block go to the edge bins ...
+		return i;
+	};
+	// ... but only if they can reach the block at all
+	std::vector<int> keep;
+	for (int q = 0; q < count; q++) {
+		bool reach = true;
+		for (int d = 0; d < 3; d++) reach = reach && b[3 * (size_t)q + d] >= lo[d] - cut && b[3 * (size_t)q + d] <= hi[d] + cut;
+		if (reach) keep.push_back(q);
+	}
+	std::vector<int> start(nbins + 1, 0);
+	std::vector<int> which(keep.size());
+	for (size_t m = 0; m < keep.size(); m++) {
+		const double *c = &b[3 * (size_t)keep[m]];
+		which[m] = (bin_of(c, 2) * rb.nb[1] + bin_of(c, 1)) * rb.nb[0] + bin_of(c, 0);
+		start[which[m] + 1]++;
+	}
+	for (int i = 0; i < nbins; i++) start[i + 1] += start[i];
+	std::vector<double> sorted(3 * std::max<size_t>(keep.size(), 1));
+	{
+		std::vector<int> fill(start.begin(), start.end() - 1);
+		for (size_t m = 0; m < keep.size(); m++) {
+			const int dst = fill[which[m]]++;
+			for (int d = 0; d < 3; d++) sorted[3 * (size_t)dst + d] = b[3 * (size_t)keep[m] + d];
+		}
+	}
+	double *dc = nullptr; int *ds = nullptr;
+	CU(cudaMalloc(&dc, sorted.size() * sizeof(double)));
+	CU(cudaMalloc(&ds, start.size() * sizeof(int)));
+	CU(cudaMemcpyAsync(dc, sorted.data(), sorted.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+	CU(cudaMemcpyAsync(ds, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
 	long long total = (long long)g.n1 * g.n2 * g.n3;
 	const int threads = 256;
 	long long blocks = (total + threads - 1) / threads;
-	PFT_LAUNCH(rasterise_kernel, dim3((unsigned)blocks), dim3(threads), 3 * threads * sizeof(double), s->stream,
-		s->gl, d, d + count, d + 2 * (size_t)count, count, g.n1, g.n2, g.n3, g.px, g.plane,
+	PFT_LAUNCH(rasterise_kernel, dim3((unsigned)blocks), dim3(threads), 0, s->stream,
+		s->gl, dc, ds, rb, g.n1, g.n2, g.n3, g.px, g.plane,
 		cs.first_row, cs.total_n3, cs.L1, cs.L2, cs.L3, cs.param[P_xi_gl], cs.param[P_ball_radius]);
 	s->st.kernel_launches++;
 	CU(cudaGetLastError());
-	int rc = (s->cs.nranks > 1) ? exchange_pair(s, s->gl, nullptr) : 0;
+	int rc = (s->cs.nranks > 1 && !s->group) ? exchange_pair(s, s->gl, nullptr) : 0;
 	CU(cudaStreamSynchronize(s->stream));
-	cudaFree(d);
+	cudaFree(dc); cudaFree(ds);
+	s->k1_valid = false;            // K1 = f(t, x) was evaluated with the old glass field
 	return rc;
 }
 
@@ -1037,7 +1153,7 @@ extern "C" int pft_ice_fraction(pft_solver *s, double *fraction)
 	CU(cudaMalloc(&d, sizeof h));
 	CU(cudaMemsetAsync(d, 0, sizeof h, s->stream));
 	const Geom &g = s->g;
-	PFT_LAUNCH(ice_count_kernel, dim3(148 * 4), dim3(256), 0, s->stream, s->arr[A_X][1], g.n1, g.n2, g.n3, g.px, g.plane, d);
+	PFT_LAUNCH(ice_count_kernel, dim3(148 * 4), dim3(256), 0, s->stream, field_ptr(s, 1), g.n1, g.n2, g.n3, g.px, g.plane, d);
 	s->st.kernel_launches++;
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, s->stream));
@@ -1055,23 +1171,25 @@ extern "C" int pft_rhs_host(pft_solver *s, double t, const double *w, double *dw
 	if (!s || !w || !dw) return fail(PFT_EINVAL, "null argument");
 	int rc = pft_upload(s, w);
 	if (rc) return rc;
-	pft_system dummy;
-	memset(&dummy, 0, sizeof dummy);
-	rc = launch_stage(s, 1, t, 0.0, 0.0, A_X, A_K1, nullptr, &dummy, 0.0, 1.0);
+	// equation.c:96-111
+	const double dir = t < s->cs.param[P_phase_switch_time] ? s->cs.param[P_top_temp1] : s->cs.param[P_top_temp2];
+	rc = launch_stage(s, 1, &dir);
 	if (rc) return rc;
 	s->st.rhs_evals++;
-	rc = ensure_stage(s);
-	if (rc) return rc;
-	const long long SIZE = s->padded / PFT_NVAR;
-	CU(cudaMemcpyAsync(s->stage_buf, dw, (size_t)s->padded * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-	if (s->heat) repack(s, s->stage_buf, s->arr[A_K1][0], 1);
-	repack(s, s->stage_buf + SIZE, s->arr[A_K1][1], 1);
-	CU(cudaMemcpyAsync(dw, s->stage_buf, (size_t)s->padded * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+	const long long SIZE = s->padded / PFT_NVAR, rowsize = (long long)s->N1 * s->N2;
+	// interior nodes of dw: through the staging image, ghost nodes of dw untouched
+	for (int q = 0; q < 2; q++) {
+		if (q == 0 && !s->heat) continue;
+		double *st = s->stage_buf + q * SIZE;
+		CU(cudaMemcpyAsync(st + PFT_BT * rowsize, dw + q * SIZE + PFT_BT * rowsize, (size_t)(s->g.n3 * rowsize) * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+		repack(s, st, s->arr[A_K1][q], 1, 0, s->g.n3);
+		CU(cudaMemcpyAsync(dw + q * SIZE + PFT_BT * rowsize, st + PFT_BT * rowsize, (size_t)(s->g.n3 * rowsize) * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+		s->stage_shell[q] = false;
+	}
 	CU(cudaStreamSynchronize(s->stream));
 	// du/dt == 0 in calc_mode 10/11 and dgl/dt == 0 always (equation.c:708,731): interior rows only
 	{
-		const int N1 = s->N1, N2 = s->N2;
-		const long long rowsize = (long long)N1 * N2;
+		const int N1 = s->N1;
 		for (int q = 0; q < PFT_NVAR; q++) {
 			if (q == 1 || (q == 0 && s->heat)) continue;
 			for (int k = 0; k < s->g.n3; k++)
@@ -1086,13 +1204,6 @@ extern "C" int pft_rhs_host(pft_solver *s, double t, const double *w, double *dw
 // ------------------------------------------------------------------------------------------
 // the integrator
 
-#define CMD_h_TOO_SMALL 1
-#define CMD_NAN         2
-#define CMD_UPDATE      4
-#define CMD_FINISHED    8
-#define CMD_NEXTFINISH  16
-#define CMD_BREAK       32
-
 static inline double host_ms()
 {
 	struct timespec ts;
@@ -1100,19 +1211,55 @@ static inline double host_ms()
 	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-static int wait_slot(pft_solver *s, unsigned long long seq)
+static inline void cpu_relax()
 {
-	volatile unsigned long long *p = &s->slot->seq;
-	unsigned long spins = 0;
-	while (*p != seq) {
-		_mm_pause();
-		if ((++spins & 0xfffff) == 0) {
+#if defined(__x86_64__) || defined(__i386__)
+	__builtin_ia32_pause();
+#elif defined(__aarch64__)
+	asm volatile("yield");
+#endif
+}
+
+// Waits until the device has advanced the sequence word to `target`.  Polls briefly, then SLEEPS between looks:
+// with attempts enqueued ahead the host has nothing to do, and a core spinning per GPU buys nothing.
+// spin_first: polls before the first sleep (depth-1 modes wait for every single attempt and want the low latency).
+static int wait_seq(pft_solver *s, const volatile unsigned long long *p, unsigned long long target, unsigned spin_first)
+{
+	unsigned long polls = 0;
+	while (*p < target) {
+		if (++polls <= spin_first) { cpu_relax(); continue; }
+		struct timespec ts = {0, 20000};
+		nanosleep(&ts, nullptr);
+		if ((polls & 0xff) == 0) {
 			cudaError_t e = cudaStreamQuery(s->stream);
 			if (e != cudaSuccess && e != cudaErrorNotReady)
-				return fail(PFT_ECUDA, "device fault while waiting for stage 5: %s", cudaGetErrorString(e));
-			if (e == cudaSuccess && *p != seq)
-				return fail(PFT_ESTATE, "stream idle but stage 5 never published its result (seq %llu)", seq);
+				return fail(PFT_ECUDA, "device fault while waiting for an attempt to finish: %s", cudaGetErrorString(e));
+			if (e == cudaSuccess && *p < target)
+				return fail(PFT_ESTATE, "stream idle but the attempt never published its result (sequence %llu < %llu)", (unsigned long long)*p, target);
 		}
+	}
+	__atomic_thread_fence(__ATOMIC_ACQUIRE);
+	return 0;
+}
+
+// the launches of ONE attempt: [S1 (skipped on the device while K1 is valid), S2, S3, S4, S5 (+ the decision)]
+static int enqueue_attempt(pft_solver *s, int live_cur)
+{
+	const bool nccl_mode = s->cs.nranks > 1 && !s->p2p;
+	const int outs[5] = {A_K1, A_A3, A_K3, A_K4, live_cur ? A_X : A_XN};
+	int rc;
+	for (int stage = 1; stage <= 5; stage++) {
+		if ((rc = launch_stage(s, stage))) return rc;
+		if (nccl_mode && (rc = exchange_pair(s, s->heat ? s->arr[outs[stage - 1]][0] : nullptr, s->arr[outs[stage - 1]][1]))) return rc;
+	}
+	if (nccl_mode) {
+		// the global error maximum: MPI_Allreduce(MAX), RK_MPI_SAsolver_hybrid2.c:572
+		double *red = (double *)((char *)s->ctl + offsetof(StepCtl, red));
+		ncclResult_t r_ = g_nccl.AllReduce(red, red, 2, ncclDouble, ncclMax, s->comm, s->stream);
+		if (r_ != ncclSuccess) return fail(PFT_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r_));
+		if (s->dev_pow) PFT_LAUNCH(ctl_decide_kernel, dim3(1), dim3(1), 0, s->stream, s->ctl, s->slot_dev, (const PowTables *)s->tab_dev, 0.0, 0);
+		else PFT_LAUNCH(ctl_publish_eps_kernel, dim3(1), dim3(1), 0, s->stream, s->ctl, s->slot_dev);
+		s->st.kernel_launches++;
 	}
 	return 0;
 }
@@ -1122,143 +1269,90 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 	if (!s || !sys) { fail(PFT_EINVAL, "null argument"); return PFT_SOLVE_BADSYSTEM; }
 	if (sys->delta <= 0) { fail(PFT_EINVAL, "delta <= 0"); return PFT_SOLVE_BADSYSTEM; }        // hybrid2.c:286
 	if (cudaSetDevice(s->device) != cudaSuccess) return fail(PFT_ECUDA, "cudaSetDevice failed");
+	if (s->cs.nranks > 1 && !s->p2p && !s->have_comm) return fail(PFT_ESTATE, "nranks > 1 but pft_comm_init was not called");
+	if (!s->params_ok) build_params(s);
 
-	double t = sys->t, h = sys->h, new_h = 0.0;
-	const double h_min = sys->h_min, delta = sys->delta;
-	int command = 0;
-	long attempts = 0;
-	int xc = A_X, xn = A_XN;              // current / candidate state pair (swapped on accept)
-	const bool multi = s->cs.nranks > 1;
+	const bool nccl_mode = s->cs.nranks > 1 && !s->p2p;
+	const bool host_pow = !s->dev_pow;
+	const bool callback = sys->service != nullptr;
+	const int depth = (nccl_mode || host_pow || callback || s->profile) ? 1 : s->depth;
+	const unsigned spin_first = depth == 1 ? 200000u : 64u;
 	int rc = 0, ret = PFT_SOLVE_DONE;
-	double t_host = 0.0;
+	bool interrupted = false;
 
-	sys->last_nan = 0;                    // :316
+	// ---- the control block of this call (RK_MPI_SAsolver_hybrid2.c:316-325), written by the host while the device is idle
+	StepCtl &c = *s->ctl_host;
+	memset(&c, 0, sizeof c);
+	c.t = sys->t; c.h = sys->h;
+	c.final_time = final_time; c.h_min = sys->h_min; c.delta = sys->delta;
+	c.delta_local = sys->delta_local ? 1 : 0; c.handle_nan = sys->handle_nan ? 1 : 0;
+	c.recompute_k1 = (s->flags & PFT_FLAG_RECOMPUTE_K1) ? 1 : 0;
+	c.steps = sys->steps; c.steps_total = sys->steps_total; c.rhs_evals = sys->rhs_evals;
+	c.max_attempts = sys->max_attempts;
+	c.switch_time = s->cs.param[P_phase_switch_time]; c.top_temp1 = s->cs.param[P_top_temp1]; c.top_temp2 = s->cs.param[P_top_temp2];
+	c.cur = s->cur; c.aseq = s->aseq;
+	c.skip1 = (s->k1_valid && s->k1_t == sys->t && !c.recompute_k1) ? 1 : 0;                      // :373
+	ctl_begin(c);
+	sys->last_nan = 0;                                                                           // :316
+	const long rhs0 = sys->rhs_evals, steps0 = sys->steps;
 
-	// :319-325
-	if ((final_time > t && h < 0) || (final_time < t && h > 0)) h *= -1;
-	if (h == 0 || fabs(final_time - t) <= fabs(h)) { h = final_time - t; command |= CMD_FINISHED; }
-
+	if (cudaMemcpyAsync(s->ctl, s->ctl_host, sizeof(StepCtl), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return fail(PFT_ECUDA, "control block upload failed");
 	cudaEventRecord(s->ev0, s->stream);
-	t_host = host_ms();
 
-	if (!(s->k1_valid && s->k1_t == t) || (s->flags & PFT_FLAG_RECOMPUTE_K1)) {
-		if ((rc = launch_stage(s, 1, t, 0.0, 0.0, xc, A_K1, nullptr, sys, 0.0, 1.0))) goto device_error;   // :373
-		sys->rhs_evals++; s->st.rhs_evals++;
+	const unsigned long long seq0 = s->aseq;
+	unsigned long long done = seq0, enq = seq0;
+	const unsigned long long budget = sys->max_attempts > 0 ? (unsigned long long)sys->max_attempts : ~0ull;
+	int live_cur = s->cur;                 // depth-1 modes: the host follows StepCtl.cur attempt by attempt
+	int status = ST_RUNNING;
+	HostSlot last;
+	memset(&last, 0, sizeof last);
+	double t_mark = host_ms();
+
+	while (status == ST_RUNNING) {
+		// ---- keep the launch queue filled: the window opens up from one attempt (a solve call that needs a single
+		//      attempt -- fixed-step mode -- enqueues exactly one) to `depth`
+		const unsigned long long window = std::min<unsigned long long>((unsigned long long)depth, 1ull + (done - seq0));
+		while (enq - done < window && enq - seq0 < budget) {
+			if ((rc = enqueue_attempt(s, live_cur))) goto device_error;
+			enq++;
+		}
+		if (enq == done) { rc = fail(PFT_ESTATE, "attempt budget exhausted but the device did not stop"); goto device_error; }
+		{ const double now = host_ms(); s->st.host_launch_ms += now - t_mark; t_mark = now; }
+
+		if (host_pow) {
+			// the device published the global error maximum and waits for pow() (pft_pow.h explains when)
+			if ((rc = wait_seq(s, &s->slot->seq_eps, done + 1, spin_first))) goto device_error;
+			double max_eps = s->slot->eps;
+			if (s->slot->delta_local) max_eps *= s->slot->h3_attempt;                              // :578
+			const double pw = (max_eps > 0.0) ? pow(sys->delta / max_eps, 0.2) : 0.0;              // :580
+			PFT_LAUNCH(ctl_decide_kernel, dim3(1), dim3(1), 0, s->stream, s->ctl, s->slot_dev, (const PowTables *)nullptr, pw, 1);
+			s->st.kernel_launches++;
+		}
+		if ((rc = wait_seq(s, &s->slot->seq, done + 1, spin_first))) goto device_error;
+		{ const double now = host_ms(); s->st.host_wait_ms += now - t_mark; t_mark = now; }
+		const unsigned long long newdone = s->slot->seq;
+		__atomic_thread_fence(__ATOMIC_ACQUIRE);
+		status = *(volatile int *)&s->slot->status;
+
+		if (depth == 1) {
+			// nothing is in flight: the slot is stable.  Follow the attempt the way the reference's master does.
+			last = *s->slot;
+			live_cur = last.cur;
+			status = last.status;
+			if (callback && last.accept) {                                                       // :676-705
+				sys->t = last.t; sys->h = last.h_attempt;
+				sys->steps = (long)last.steps; sys->steps_total = (long)last.steps_total;
+				const int stop = sys->service(final_time, last.t, last.h_attempt, (long)last.steps, (long)last.steps_total, sys->service_ctx);
+				if (last.status == ST_DONE) { /* FINISHED wins over BREAK (:695 before :697) */ }
+				else if (stop) { interrupted = true; done = newdone; break; }
+			}
+			if (callback && (last.command & CMD_NEXTFINISH) && !(last.command & CMD_NAN) && last.status != ST_DONE) sys->h = last.new_h;   // :754
+			if (callback && last.status == ST_BUDGET && !(last.command_next & CMD_FINISHED)) sys->h = last.h_next;
+		}
+		done = newdone;
 	}
-	s->k1_valid = false;
 
-	for (;;) {
-		const double h2 = h / 2.0, h3 = h / 3.0, h6 = h / 6.0, h8 = h / 8.0;    // :355
-		const double eps_scale = fabs(h3);
-
-		if ((rc = launch_stage(s, 2, t + h3, h3, h6, xc, A_A3, nullptr, sys, 0.0, 1.0))) goto device_error;   // :378-409
-		if ((rc = launch_stage(s, 3, t + h3, 0.0, 0.0, xc, A_K3, nullptr, sys, 0.0, 1.0))) goto device_error; // :412
-		if ((rc = launch_stage(s, 4, t + h2, h8, 0.0, xc, A_K4, nullptr, sys, 0.0, 1.0))) goto device_error;  // :417-432
-		if ((rc = launch_stage(s, 5, t + h, h, h3, xc, xn, nullptr, sys, fabs(h), eps_scale))) goto device_error; // :437-524,657-668
-		sys->rhs_evals += 4; s->st.rhs_evals += 4;
-		const unsigned long long seq = s->seq;
-
-		double eps; int nonfinite;
-		if (!multi || s->p2p) {
-			// (peer path: stage 5's last CTA has formed the global max + decision on the device, the role of
-			// MPI_Allreduce(MAX), :572)
-			if (s->speculate)          // K1 of the next step, gated on the device-side accept flag
-				if ((rc = launch_stage(s, 1, t + h, 0.0, 0.0, xn, A_K1, &s->ctl->accept, sys, 0.0, 1.0))) goto device_error;
-			const double tw = host_ms();
-			s->st.host_launch_ms += tw - t_host;
-			if ((rc = wait_slot(s, seq))) goto device_error;
-			t_host = host_ms();
-			s->st.host_wait_ms += t_host - tw;
-			eps = s->slot->eps; nonfinite = s->slot->nonfinite;
-		} else {
-			// NCCL path (PFT_COMM=nccl, or no peer access): global max over the slabs through the host
-			if ((rc = wait_slot(s, seq))) goto device_error;
-			s->red_host[0] = s->slot->eps; s->red_host[1] = (double)s->slot->nonfinite;
-			if (cudaMemcpyAsync(s->red, s->red_host, 2 * sizeof(double), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) { rc = fail(PFT_ECUDA, "memcpy"); goto device_error; }
-			{
-				ncclResult_t r_ = g_nccl.AllReduce(s->red, s->red, 2, ncclDouble, ncclMax, s->comm, s->stream);
-				if (r_ != ncclSuccess) { rc = fail(PFT_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r_)); goto device_error; }
-			}
-			if (cudaMemcpyAsync(s->red_host, s->red, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) { rc = fail(PFT_ECUDA, "memcpy"); goto device_error; }
-			if (cudaStreamSynchronize(s->stream) != cudaSuccess) { rc = fail(PFT_ECUDA, "sync after allreduce: %s", cudaGetErrorString(cudaGetLastError())); goto device_error; }
-			eps = s->red_host[0]; nonfinite = s->red_host[1] != 0.0;
-		}
-		if (s->profile) drain_timers(s);
-
-		sys->steps_total++; s->st.attempts++;                                    // :460
-		attempts++;
-
-		double max_eps = eps;
-		if (sys->delta_local) max_eps *= eps_scale;                              // :578
-		new_h = ((max_eps > 0.0) ? pow((delta / max_eps), 0.2) * 0.8 : 2.0) * h; // :580
-
-		if (sys->handle_nan && nonfinite) {                                      // :493-503
-			command |= CMD_NAN;
-			if (h / (final_time - t) < 1e-11) command |= CMD_h_TOO_SMALL;
-		}
-		if (max_eps < delta || fabs(h) < h_min) {                                // :599-611
-			command |= CMD_UPDATE;
-			if (fabs(final_time - (t + h)) <= fabs(new_h)) command |= CMD_NEXTFINISH;
-		}
-		if (!multi || s->p2p) {
-			const int host_accept = ((command & CMD_UPDATE) && !(command & CMD_NAN)) ? 1 : 0;
-			if (host_accept != s->slot->accept) {
-				rc = fail(PFT_ESTATE, "device/host acceptance mismatch (eps %.17g delta %.17g h %.17g)", eps, delta, h);
-				goto device_error;
-			}
-		}
-
-		if (command & CMD_NAN) {                                                 // :626-646
-			sys->last_nan = 1;
-			if (command & CMD_h_TOO_SMALL) { sys->t = t; s->k1_valid = true; s->k1_t = t; ret = PFT_SOLVE_NAN; goto done; }
-			h /= 10;
-			command = 0;
-			if (s->flags & PFT_FLAG_RECOMPUTE_K1) {
-				if ((rc = launch_stage(s, 1, t, 0.0, 0.0, xc, A_K1, nullptr, sys, 0.0, 1.0))) goto device_error;
-				sys->rhs_evals++; s->st.rhs_evals++;
-			}
-		} else {
-			if (command & CMD_UPDATE) {                                          // :651-734
-				t += h;
-				std::swap(xc, xn);
-				sys->steps++; s->st.accepted++;
-				if ((!multi || s->p2p) && s->speculate) { sys->rhs_evals++; s->st.rhs_evals++; }     // the gated stage 1 ran
-				else {
-					if ((rc = launch_stage(s, 1, t, 0.0, 0.0, xc, A_K1, nullptr, sys, 0.0, 1.0))) goto device_error;
-					sys->rhs_evals++; s->st.rhs_evals++;
-				}
-				if (sys->service) {
-					sys->t = t; sys->h = h;
-					if (sys->service(final_time, t, h, sys->steps, sys->steps_total, sys->service_ctx)) command |= CMD_BREAK;
-				}
-				if (command & CMD_FINISHED) break;
-				if (command & CMD_BREAK) { sys->t = t; sys->h = new_h; ret = PFT_SOLVE_INTERRUPTED; goto done_k1; }
-			} else if (s->flags & PFT_FLAG_RECOMPUTE_K1) {
-				if ((rc = launch_stage(s, 1, t, 0.0, 0.0, xc, A_K1, nullptr, sys, 0.0, 1.0))) goto device_error;
-				sys->rhs_evals++; s->st.rhs_evals++;
-			}
-			if (command & CMD_NEXTFINISH) {                                      // :745-760
-				sys->h = new_h;
-				h = final_time - t;
-				command = CMD_FINISHED;
-			} else {
-				command = 0;
-				h = new_h;
-			}
-		}
-
-		if (sys->max_attempts > 0 && attempts >= sys->max_attempts) {
-			sys->t = t;
-			if (!(command & CMD_FINISHED)) sys->h = h;
-			ret = PFT_SOLVE_BUDGET;
-			goto done_k1;
-		}
-	}
-	sys->t = t;                                                                  // :768
-
-done_k1:
-	s->k1_valid = true; s->k1_t = t;      // K1 == f(t, x) holds at every exit that reaches here
-done:
+	// ---- exit: drain the queue (launches beyond the end return at once), read the final state
 	cudaEventRecord(s->ev1, s->stream);
 	if (cudaStreamSynchronize(s->stream) != cudaSuccess) { rc = fail(PFT_ECUDA, "stream sync at solve exit: %s", cudaGetErrorString(cudaGetLastError())); goto device_error; }
 	if (s->profile) drain_timers(s);
@@ -1267,22 +1361,199 @@ done:
 		cudaEventElapsedTime(&ms, s->ev0, s->ev1);
 		s->st.device_ms_total = ms;
 	}
-	// keep the accepted state in pair A_X so that upload/download/debug see a fixed place
-	if (xc != A_X) {
-		std::swap(s->arr[A_X][0], s->arr[A_XN][0]);
-		std::swap(s->arr[A_X][1], s->arr[A_XN][1]);
-		std::swap(s->tmap[A_X][0], s->tmap[A_XN][0]);
-		std::swap(s->tmap[A_X][1], s->tmap[A_XN][1]);
-		std::swap(s->off[A_X][0], s->off[A_XN][0]);
-		std::swap(s->off[A_X][1], s->off[A_XN][1]);
+	last = *s->slot;
+	{
+		const long n_att = (long)(last.seq - seq0);
+		s->st.attempts += n_att;
+		s->st.accepted += (long)last.steps - steps0;
+		s->st.noop_launches += (long)(enq - last.seq) * 5;
+		// (stage launches that returned at once are not right-hand-side evaluations)
+		long rhs = (long)last.rhs_evals;
+		if (interrupted && last.status == ST_RUNNING) rhs -= 1;      // stage 1 of the next attempt was counted but never enqueued
+		s->st.rhs_evals += rhs - rhs0;
+		sys->rhs_evals = rhs;
 	}
+	if (!callback) { if (last.sys_h_set) sys->h = last.sys_h; }
+	else if (interrupted) sys->h = last.new_h;                                                   // :701
+	sys->t = last.t;                                                                             // :768 / :700 / :634
+	sys->steps = (long)last.steps; sys->steps_total = (long)last.steps_total;
+	sys->last_nan = last.last_nan;
+	s->cur = last.cur;
+	s->aseq = last.seq;
+	s->k1_valid = (last.seq > seq0) ? (last.accept == 0) : s->k1_valid;     // after a rejected attempt K1 == f(t, x) still holds
+	s->k1_t = last.t;
+	if (interrupted) ret = PFT_SOLVE_INTERRUPTED;
+	else if (last.status == ST_BUDGET) ret = PFT_SOLVE_BUDGET;
+	else if (last.status == ST_NAN) ret = PFT_SOLVE_NAN;
 	return ret;
 
 device_error:
 	cudaStreamSynchronize(s->stream);
 	drain_timers(s);
+	// what the device did to the control block is unknown: bring the host's mirror back in step with it
+	if (s->slot->seq >= s->aseq) { s->aseq = s->slot->seq; s->cur = s->slot->cur; }
 	s->k1_valid = false;
 	return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// one host process, several GPUs
+
+extern "C" int pft_group_size(const pft_group *g) { return g ? g->n : 0; }
+extern "C" pft_solver *pft_group_member(pft_group *g, int r) { return (g && r >= 0 && r < g->n) ? g->member[r] : nullptr; }
+
+extern "C" int pft_group_destroy(pft_group *g)
+{
+	if (!g) return 0;
+	for (pft_solver *m : g->member) pft_destroy(m);
+	delete g;
+	return 0;
+}
+
+extern "C" int pft_group_create(const pft_case *whole, int ngpus, const int *devices, unsigned flags, pft_group **out)
+{
+	if (!whole || !out || ngpus < 1) return fail(PFT_EINVAL, "bad argument");
+	*out = nullptr;
+	if (whole->nranks != 1 || whole->rank != 0) return fail(PFT_EINVAL, "pft_group_create takes the whole block of a single-rank run");
+	if (ngpus > PFT_MAX_RANKS) return fail(PFT_EINVAL, "at most %d GPUs per group", PFT_MAX_RANKS);
+	if (whole->n3 / ngpus < 1) return fail(PFT_EINVAL, "%d planes cannot be cut into %d slabs", whole->n3, ngpus);
+	pft_group *g = new (std::nothrow) pft_group();
+	if (!g) return fail(PFT_ENOMEM, "out of host memory");
+	g->n = ngpus; g->whole = *whole;
+	g->user_service = nullptr; g->user_ctx = nullptr;
+	g->cb_seq.store(-1); g->cb_val.store(0);
+	int first = whole->first_row;
+	for (int r = 0; r < ngpus; r++) {
+		pft_case c = *whole;
+		c.rank = r; c.nranks = ngpus;
+		c.n3 = slab_n3(whole->n3, ngpus, r);          // intertrack.c:1780-1787
+		c.first_row = first;
+		first += c.n3;
+		// (total_n3 stays the whole grid's: the z grid spacing comes from it, equation.c:607)
+		pft_solver *m = nullptr;
+		int rc = pft_create(&c, devices ? devices[r] : r, flags, &m);
+		if (rc) { pft_group_destroy(g); return rc; }
+		m->group = g;
+		g->member.push_back(m);
+	}
+	// the slab-local geometry above deviates from a true ngpus-rank run in one respect only: the group owns the
+	// physical z boundaries of `whole`, which may itself be a slab of a larger multi-process run -- not supported yet
+	if (ngpus > 1) {
+#ifndef PFT_CUDA_EMU
+		for (int r = 0; r < ngpus; r++)
+			for (int q = 0; q < ngpus; q++) {
+				if (q == r || g->member[q]->device == g->member[r]->device) continue;
+				int can = 0;
+				cudaDeviceCanAccessPeer(&can, g->member[r]->device, g->member[q]->device);
+				if (!can) { pft_group_destroy(g); return fail(PFT_ENODEVICE, "device %d cannot access device %d: the in-process group needs peer access (NVLink)", g->member[r]->device, g->member[q]->device); }
+				cudaSetDevice(g->member[r]->device);
+				cudaError_t e = cudaDeviceEnablePeerAccess(g->member[q]->device, 0);
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { pft_group_destroy(g); return fail(PFT_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); }
+				cudaGetLastError();
+			}
+#endif
+		for (int r = 0; r < ngpus; r++) {
+			pft_solver *m = g->member[r];
+			for (int q = 0; q < ngpus; q++) { m->peer_base[q] = g->member[q]->slab; m->peer_n3[q] = g->member[q]->cs.n3; }
+			m->p2p = true; m->ipc = false;
+			m->params_ok = false;
+		}
+	}
+	*out = g;
+	return 0;
+}
+
+// the slabs of ONE padded host array: slab r's padded plane 0 is the whole block's padded plane (first_row_r - first_row_0)
+extern "C" int pft_group_upload(pft_group *g, const double *x, unsigned mask)
+{
+	if (!g || !x) return fail(PFT_EINVAL, "null argument");
+	const pft_case &w = g->whole;
+	const long long rowsize = (long long)(w.n1 + 2 * PFT_BT) * (w.n2 + 2 * PFT_BT), SIZEW = rowsize * (w.n3 + 2 * PFT_BT);
+	for (int r = 0; r < g->n; r++) {
+		pft_solver *m = g->member[r];
+		CU(cudaSetDevice(m->device));
+		int rc = ensure_stage(m);
+		if (rc) return rc;
+		const long long row0 = m->cs.first_row - w.first_row;
+		for (int q = 0; q < PFT_NVAR; q++)
+			if ((mask >> q) & 1u)
+				if ((rc = upload_var(m, x + q * SIZEW + row0 * rowsize, q, r > 0, r < g->n - 1))) return rc;
+		CU(cudaGetLastError());
+		m->k1_valid = false;
+	}
+	for (int r = 0; r < g->n; r++) { CU(cudaSetDevice(g->member[r]->device)); CU(cudaStreamSynchronize(g->member[r]->stream)); }
+	return 0;
+}
+
+extern "C" int pft_group_download(pft_group *g, double *x, unsigned mask)
+{
+	if (!g || !x) return fail(PFT_EINVAL, "null argument");
+	const pft_case &w = g->whole;
+	const long long rowsize = (long long)(w.n1 + 2 * PFT_BT) * (w.n2 + 2 * PFT_BT), SIZEW = rowsize * (w.n3 + 2 * PFT_BT);
+	for (int r = 0; r < g->n; r++) {
+		pft_solver *m = g->member[r];
+		CU(cudaSetDevice(m->device));
+		int rc = ensure_stage(m);
+		if (rc) return rc;
+		const long long row0 = m->cs.first_row - w.first_row;
+		for (int q = 0; q < PFT_NVAR; q++)
+			if ((mask >> q) & 1u)
+				if ((rc = download_var(m, x + q * SIZEW + row0 * rowsize, q))) return rc;
+		CU(cudaGetLastError());
+	}
+	for (int r = 0; r < g->n; r++) { CU(cudaSetDevice(g->member[r]->device)); CU(cudaStreamSynchronize(g->member[r]->stream)); }
+	return 0;
+}
+
+// Service_Callback in a group: the callback belongs to the master (intertrack.c:2173 installs it on rank 0 only);
+// every slab stops after the same accepted step, so slab 0's worker asks the user and the others take its answer
+// (the reference re-broadcasts the command word after the callback, RK_MPI_SAsolver_hybrid2.c:690).
+static int group_service_leader(double final_time, double t, double h, long steps, long steps_total, void *ctx)
+{
+	pft_group *g = (pft_group *)ctx;
+	const int v = g->user_service(final_time, t, h, steps, steps_total, g->user_ctx) ? 1 : 0;
+	g->cb_val.store(v, std::memory_order_relaxed);
+	g->cb_seq.store(steps_total, std::memory_order_release);
+	return v;
+}
+
+static int group_service_follower(double, double, double, long, long steps_total, void *ctx)
+{
+	pft_group *g = (pft_group *)ctx;
+	while (g->cb_seq.load(std::memory_order_acquire) != steps_total) cpu_relax();
+	return g->cb_val.load(std::memory_order_relaxed);
+}
+
+extern "C" int pft_group_solve(pft_group *g, pft_system *sys, double final_time)
+{
+	if (!g || !sys) { fail(PFT_EINVAL, "null argument"); return PFT_SOLVE_BADSYSTEM; }
+	if (g->n == 1) return pft_solve(g->member[0], sys, final_time);
+	std::vector<pft_system> ss(g->n, *sys);
+	std::vector<int> rcs(g->n, 0);
+	std::vector<std::string> errs(g->n);
+	g->user_service = sys->service; g->user_ctx = sys->service_ctx;
+	g->cb_seq.store(-1);
+	for (int r = 0; r < g->n; r++) {
+		if (sys->service) { ss[r].service = (r == 0) ? group_service_leader : group_service_follower; ss[r].service_ctx = g; }
+	}
+	std::vector<std::thread> th;
+	for (int r = 1; r < g->n; r++)
+		th.emplace_back([&, r]() { rcs[r] = pft_solve(g->member[r], &ss[r], final_time); if (rcs[r] < 0) errs[r] = pft_last_error(); });
+	rcs[0] = pft_solve(g->member[0], &ss[0], final_time);
+	if (rcs[0] < 0) errs[0] = pft_last_error();
+	for (auto &t : th) t.join();
+	for (int r = 0; r < g->n; r++)
+		if (rcs[r] != rcs[0] || ss[r].t != ss[0].t || ss[r].steps_total != ss[0].steps_total) {
+			if (rcs[r] < 0 && rcs[r] != PFT_SOLVE_NAN) return fail(rcs[r], "slab %d: %s", r, errs[r].c_str());
+			if (rcs[0] < 0 && rcs[0] != PFT_SOLVE_NAN) return fail(rcs[0], "slab 0: %s", errs[0].c_str());
+			return fail(PFT_ESTATE, "the slabs of the group disagree (slab %d: code %d t %.17g attempts %ld; slab 0: code %d t %.17g attempts %ld)",
+			            r, rcs[r], ss[r].t, ss[r].steps_total, rcs[0], ss[0].t, ss[0].steps_total);
+		}
+	if (rcs[0] < 0 && rcs[0] != PFT_SOLVE_NAN && rcs[0] != PFT_SOLVE_BADSYSTEM) return fail(rcs[0], "slab 0: %s", errs[0].c_str());
+	const pft_service_fn keep_fn = sys->service; void *keep_ctx = sys->service_ctx;
+	*sys = ss[0];
+	sys->service = keep_fn; sys->service_ctx = keep_ctx;
+	return rcs[0];
 }
 
 extern "C" int pft_get_stats(pft_solver *s, pft_stats *out)
@@ -1299,5 +1570,6 @@ extern "C" int pft_reset_stats(pft_solver *s)
 	memset(&s->st, 0, sizeof s->st);
 	s->st.tile_x = keep.tile_x; s->st.tile_y = keep.tile_y; s->st.z_chunk = keep.z_chunk;
 	s->st.threads = keep.threads; s->st.grid_blocks = keep.grid_blocks; s->st.bytes_per_field = keep.bytes_per_field;
+	s->st.device_pow = keep.device_pow; s->st.runahead = keep.runahead;
 	return 0;
 }

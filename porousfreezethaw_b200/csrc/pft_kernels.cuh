@@ -38,6 +38,8 @@
 #include <stdint.h>
 #include <math.h>
 
+#include "pft_ctl.h"
+
 // dynamic shared memory (tests/cuda_emu/ redefines this for its CPU emulation of the kernels)
 #ifndef PFT_DYN_SMEM
 #define PFT_DYN_SMEM(type, name) extern __shared__ type name[]
@@ -61,23 +63,6 @@ struct Geom {
 	int zc;                   // planes per z-chunk (gridDim.z chunks)
 };
 
-// device-resident control block of the error reduction / step acceptance
-struct Ctl {
-	unsigned long long eps_bits;   // running max of the error estimate (bit pattern of a non-negative double)
-	unsigned int ticket;           // finished-CTA counter of the current stage-5 launch
-	int accept;                    // decision of the last attempt (read by the speculative stage 1)
-	int nonfinite;                 // a non-finite error component was seen (NaN handling)
-	int pad;
-};
-
-// host-mapped result slot (pinned, zero-copy): written by the last CTA of stage 5
-struct HostSlot {
-	unsigned long long seq;
-	double eps;
-	int accept;
-	int nonfinite;
-};
-
 constexpr int PFT_MAX_RANKS = 16;
 
 // one rank's local error maximum of an attempt, as seen by every rank (peer-written)
@@ -95,43 +80,78 @@ struct SyncBlock {
 	EpsSlot slot[2][PFT_MAX_RANKS];      // [attempt & 1][rank]
 };
 
-// peer-memory halo exchange (one process per GPU, slabs mapped into each other with CUDA IPC);
-// all zero on a single GPU and on the NCCL path
+// peer-memory halo exchange (one process per GPU with CUDA IPC, or one process driving several GPUs with
+// peer access); all zero on a single GPU and on the NCCL path
 struct PeerArgs {
-	double *lo_u, *lo_p;                 // lower neighbour's upper ghost plane of this stage's output pair
-	double *hi_u, *hi_p;                 // upper neighbour's lower ghost plane
+	// the neighbours' ghost planes of this stage's output pair.  Stage 5 writes the candidate pair,
+	// which alternates with StepCtl.cur: index [cur ^ 1]; the other stages use index 0.
+	double *lo_u[2], *lo_p[2];           // lower neighbour's upper ghost plane
+	double *hi_u[2], *hi_p[2];           // upper neighbour's lower ghost plane
 	unsigned long long *lo_flag, *hi_flag;   // the neighbours' halo_flag entries this rank signals
 	const unsigned long long *my_flags;  // this rank's halo_flag[2]
 	unsigned int *tickets;               // finished boundary CTAs, [lower, upper]
-	unsigned long long hseq;             // sequence number of this stage launch (identical on every rank)
 	SyncBlock *ranks[PFT_MAX_RANKS];     // stage 5: every rank's sync block (error-max broadcast)
 	int rank, nranks;
 	int wait_lo, wait_hi;                // this slab has a lower / an upper neighbour
 	int nzc;                             // number of z-chunks (boundary chunks are scheduled first)
 };
 
+// how stage 5 ends
+enum { FIN_DECIDE = 0,      // the last CTA takes the step decision on the device (pft_ctl.h) and publishes it
+       FIN_PUBLISH_EPS = 1, // ... publishes the global error maximum and leaves the decision to ctl_decide_kernel
+                            //     (the host supplies pow(): the library's pow could not be reproduced, pft_pow.h)
+       FIN_STORE_LOCAL = 2 };// ... stores this slab's maximum in StepCtl.red (NCCL path: an all-reduce follows)
+
+// Launch arguments of a stage.  Nothing in here depends on the step length or on the outcome of an
+// earlier attempt: those scalars are read from the device-resident StepCtl, so the same argument
+// block serves every attempt.
 struct StageArgs {
 	PeerArgs pr;
-	const double *xu, *xp, *gl;                 // step-start state (u, p) and the static glass field
+	StepCtl *ctl;
+	double *xu[2], *xp[2];                      // the two state pairs; StepCtl.cur says which one holds x
+	const double *gl;                           // the static glass field
 	const double *k1u, *k1p, *k3u, *k3p, *k4u, *k4p;
 	const double *au, *ap;                      // stage 3: the stored stage input (aux3)
-	double *ou, *op;                            // output pair
-	double ha, hb;                              // stage 2: h3,h6   stage 4: h8   stage 5: h,h3
-	double dir_u;                               // Dirichlet temperature at this stage's time level
+	double *ou, *op;                            // output pair of stages 1-4
 	// stage 5 only
-	double delta, h_abs, h_min, eps_scale;      // eps_scale = |h3| for DELTA_LOCAL else 1 (applied as a multiply only if != 1)
-	int scale_eps, handle_nan;
-	Ctl *ctl;
 	HostSlot *slot;
-	unsigned long long seq;
+	const PowTables *tab;                       // device copy of the host library's pow tables (FIN_DECIDE)
 	unsigned int nblocks;
-	// stage 1 only: run only if *cond != 0 (speculative launch before the host's decision)
-	const int *cond;
-#ifdef PFT_TRACE
-	unsigned long long *trace;                  // development build: one timeline record per launch
-	unsigned long long *trace_cta;              // and (start, end of body, end, smid<<32|chunk) per CTA of the first launches
-#endif
+	int fin_mode;
+	int standalone, standalone_cur;             // a single right-hand-side evaluation outside the time loop (pft_rhs_host)
+	double dir_standalone;
 };
+
+// what a stage kernel reads from the control block when it starts
+struct StageScalars {
+	double ha, hb, dir_u;
+	int cur;
+	unsigned long long hseq;             // sequence number of this launch in the halo-flag protocol (same on every rank)
+};
+
+#ifndef PFT_CUDA_EMU
+template <class T> __device__ __forceinline__ T ctl_ld(const T *p) { return __ldcg(p); }
+#else
+template <class T> inline T ctl_ld(const T *p) { return *p; }
+#endif
+
+template <int STAGE>
+__device__ __forceinline__ bool stage_begin(const StageArgs &a, StageScalars &sc)
+{
+	if (a.standalone) { sc.ha = sc.hb = 0.0; sc.dir_u = a.dir_standalone; sc.cur = a.standalone_cur; sc.hseq = 0; return true; }
+	// (L2 loads: the block was written by the previous attempt's controller thread while CTAs of this
+	//  launch may already have been resident on the SM -- programmatic dependent launch)
+	const StepCtl *c = a.ctl;
+	if (ctl_ld(&c->status) != ST_RUNNING) return false;   // enqueued beyond the end of the integration: nothing to do
+	sc.cur = ctl_ld(&c->cur);
+	sc.dir_u = ctl_ld(&c->dir[STAGE - 1]);
+	sc.hseq = 5ull * ctl_ld(&c->aseq) + STAGE;
+	sc.ha = sc.hb = 0.0;
+	if (STAGE == 2) { sc.ha = ctl_ld(&c->h3); sc.hb = ctl_ld(&c->h6); }
+	if (STAGE == 4) sc.ha = ctl_ld(&c->h8);
+	if (STAGE == 5) { sc.ha = ctl_ld(&c->h); sc.hb = ctl_ld(&c->h3); }
+	return true;
+}
 
 struct KParams {
 	Consts c;
@@ -195,34 +215,35 @@ struct Raw {      // what has to be remembered of a centre cell until its output
 // Loads the stage input (su, sp) at linear index `idx`; fills `r` with the operands the output
 // combination needs (only touched members are kept alive by the compiler).
 template <int STAGE, bool HEAT, bool KEEP>
-__device__ __forceinline__ void load_state(const StageArgs &a, long long idx, double &su, double &sp, Raw<STAGE, HEAT> &r)
+__device__ __forceinline__ void load_state(const StageArgs &a, const double *xu_, const double *xp_, double ha, long long idx,
+                                           double &su, double &sp, Raw<STAGE, HEAT> &r)
 {
 	if (STAGE == 1) {
-		su = a.xu[idx];
-		sp = a.xp[idx];
+		su = xu_[idx];
+		sp = xp_[idx];
 	} else if (STAGE == 3) {
 		sp = a.ap[idx];
-		su = HEAT ? a.au[idx] : a.xu[idx];
+		su = HEAT ? a.au[idx] : xu_[idx];
 	} else if (STAGE == 2) {
-		double xp = a.xp[idx], k1p = a.k1p[idx];
-		sp = k1p * a.ha + xp;                                   // :388  q = v*h3 + w
-		double xu = a.xu[idx];
-		if (HEAT) { double k1u = a.k1u[idx]; su = k1u * a.ha + xu; if (KEEP) r.k1u = k1u; }
+		double xp = xp_[idx], k1p = a.k1p[idx];
+		sp = k1p * ha + xp;                                     // :388  q = v*h3 + w
+		double xu = xu_[idx];
+		if (HEAT) { double k1u = a.k1u[idx]; su = k1u * ha + xu; if (KEEP) r.k1u = k1u; }
 		else su = xu;
 		if (KEEP) { r.xu = xu; r.xp = xp; r.k1p = k1p; }
 	} else if (STAGE == 4) {
-		double xp = a.xp[idx], k1p = a.k1p[idx], k3p = a.k3p[idx];
-		sp = (k1p + 3.0 * k3p) * a.ha + xp;                     // :428
-		double xu = a.xu[idx];
-		if (HEAT) { double k1u = a.k1u[idx], k3u = a.k3u[idx]; su = (k1u + 3.0 * k3u) * a.ha + xu; }
+		double xp = xp_[idx], k1p = a.k1p[idx], k3p = a.k3p[idx];
+		sp = (k1p + 3.0 * k3p) * ha + xp;                       // :428
+		double xu = xu_[idx];
+		if (HEAT) { double k1u = a.k1u[idx], k3u = a.k3u[idx]; su = (k1u + 3.0 * k3u) * ha + xu; }
 		else su = xu;
 	} else {
-		double xp = a.xp[idx], k1p = a.k1p[idx], k3p = a.k3p[idx], k4p = a.k4p[idx];
-		sp = (0.5 * k1p - 1.5 * k3p + 2.0 * k4p) * a.ha + xp;   // :449
-		double xu = a.xu[idx];
+		double xp = xp_[idx], k1p = a.k1p[idx], k3p = a.k3p[idx], k4p = a.k4p[idx];
+		sp = (0.5 * k1p - 1.5 * k3p + 2.0 * k4p) * ha + xp;     // :449
+		double xu = xu_[idx];
 		if (HEAT) {
 			double k1u = a.k1u[idx], k3u = a.k3u[idx], k4u = a.k4u[idx];
-			su = (0.5 * k1u - 1.5 * k3u + 2.0 * k4u) * a.ha + xu;
+			su = (0.5 * k1u - 1.5 * k3u + 2.0 * k4u) * ha + xu;
 			if (KEEP) { r.k1u = k1u; r.k3u = k3u; r.k4u = k4u; }
 		} else su = xu;
 		if (KEEP) { r.xu = xu; r.xp = xp; r.k1p = k1p; r.k3p = k3p; r.k4p = k4p; }
@@ -253,8 +274,8 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 #else
-inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return *p; }
-inline void st_release_sys(unsigned long long *p, unsigned long long v) { *p = v; }
+inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 #endif
 
 // programmatic dependent launch (stage kernels are launched with programmatic stream serialization):
@@ -279,38 +300,21 @@ __device__ __forceinline__ int chunk_of_block(int nzc)
 	return z == 0 ? nzc - 1 : (z == 1 ? 0 : z - 1);      // the top chunk pushes its plane last: give it the head start
 }
 
-// ---- development build (-DPFT_TRACE): per-launch timeline from %globaltimer -----------------------
-// record: [0] ~first CTA start  [1] last CTA start  [2] last CTA end  [3] last lower-boundary CTA past
-// its wait  [4] same, upper  [5] longest wait (ns)  [6] lower flag published  [7] upper flag published
-// [8] stage 5: error-max exchange starts  [9] decision published  [10] longest halo_signal (ns)
-// [11..13] longest CTA body (ns) among lower-boundary / upper-boundary / interior chunks
-#ifdef PFT_TRACE
-__device__ __forceinline__ unsigned long long gtime()
-{
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	return t;
-}
-#define PFT_TRACE_MAX(a, i, v) do { if ((a).trace) atomicMax(&(a).trace[i], (unsigned long long)(v)); } while (0)
-#else
-#define PFT_TRACE_MAX(a, i, v) do { } while (0)
-#endif
-
-__device__ __forceinline__ void halo_wait(const PeerArgs &pr, bool lo, bool hi, int tid)
+__device__ __forceinline__ void halo_wait(const PeerArgs &pr, unsigned long long hseq, bool lo, bool hi, int tid)
 {
 	const bool wl = lo && pr.wait_lo, wh = hi && pr.wait_hi;
-	if (!(wl || wh)) return;
+	if (!(wl || wh) || hseq == 0) return;
 	if (tid == 0) {
-		if (wl) while (ld_acquire_sys(&pr.my_flags[0]) + 1 < pr.hseq) { }
-		if (wh) while (ld_acquire_sys(&pr.my_flags[1]) + 1 < pr.hseq) { }
+		if (wl) while (ld_acquire_sys(&pr.my_flags[0]) + 1 < hseq) { }
+		if (wh) while (ld_acquire_sys(&pr.my_flags[1]) + 1 < hseq) { }
 	}
 	__syncthreads();
 }
 
-__device__ __forceinline__ void halo_signal(const PeerArgs &pr, bool lo, bool hi, int tid)
+__device__ __forceinline__ void halo_signal(const PeerArgs &pr, unsigned long long hseq, bool lo, bool hi, int tid)
 {
 	const bool wl = lo && pr.wait_lo, wh = hi && pr.wait_hi;
-	if (!(wl || wh)) return;
+	if (!(wl || wh) || hseq == 0) return;
 	__syncthreads();                     // every thread's peer stores happen before thread 0's ticket (CTA barrier) ...
 	if (tid == 0) {
 		// ... a device-scope release per CTA, and ONE system-scope fence per side and launch, by the CTA that
@@ -319,36 +323,58 @@ __device__ __forceinline__ void halo_signal(const PeerArgs &pr, bool lo, bool hi
 		// when the boundary CTAs of a launch finish together (measured, profiles/round1_tuning.md).
 		__threadfence();
 		const unsigned int n = gridDim.x * gridDim.y;
-		if (wl && atomicAdd(&pr.tickets[0], 1u) == n - 1) { pr.tickets[0] = 0u; __threadfence_system(); st_release_sys(pr.lo_flag, pr.hseq); }
-		if (wh && atomicAdd(&pr.tickets[1], 1u) == n - 1) { pr.tickets[1] = 0u; __threadfence_system(); st_release_sys(pr.hi_flag, pr.hseq); }
+		if (wl && atomicAdd(&pr.tickets[0], 1u) == n - 1) { pr.tickets[0] = 0u; __threadfence_system(); st_release_sys(pr.lo_flag, hseq); }
+		if (wh && atomicAdd(&pr.tickets[1], 1u) == n - 1) { pr.tickets[1] = 0u; __threadfence_system(); st_release_sys(pr.hi_flag, hseq); }
 	}
 }
 
-// a skipped launch (speculative stage 1 of a rejected step) still has to advance the flags
-__device__ __forceinline__ void halo_skip(const PeerArgs &pr)
+// a skipped launch (stage 1 after a rejected attempt: K1 is still valid) still has to advance the flags
+__device__ __forceinline__ void halo_skip(const PeerArgs &pr, unsigned long long hseq)
 {
+	if (hseq == 0) return;
 	if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0) {
-		if (pr.wait_lo) st_release_sys(pr.lo_flag, pr.hseq);
-		if (pr.wait_hi) st_release_sys(pr.hi_flag, pr.hseq);
+		if (pr.wait_lo) st_release_sys(pr.lo_flag, hseq);
+		if (pr.wait_hi) st_release_sys(pr.hi_flag, hseq);
 	}
+}
+
+// where a stage writes: stages 1-4 their fixed output pair, stage 5 the candidate state pair
+struct OutPtrs {
+	double *ou, *op;
+	double *lo_u, *lo_p, *hi_u, *hi_p;   // the neighbours' ghost planes of the same pair (peer path), else null
+};
+
+template <int STAGE>
+__device__ __forceinline__ OutPtrs out_ptrs(const StageArgs &a, int cur)
+{
+	OutPtrs o;
+	const int oi = (STAGE == 5) ? (cur ^ 1) : 0;
+	o.ou = (STAGE == 5) ? a.xu[oi] : a.ou;
+	o.op = (STAGE == 5) ? a.xp[oi] : a.op;
+	o.lo_u = a.pr.lo_u[oi]; o.lo_p = a.pr.lo_p[oi];
+	o.hi_u = a.pr.hi_u[oi]; o.hi_p = a.pr.hi_p[oi];
+	return o;
 }
 
 // store one output pair value, and push it into the neighbours' ghost planes from the boundary planes
 template <bool HEAT>
-__device__ __forceinline__ void store_out(const StageArgs &a, long long o, long long col, int k, int n3, double vu, double vp)
+__device__ __forceinline__ void store_out(const OutPtrs &w, long long o, long long col, int k, int n3, double vu, double vp)
 {
-	a.op[o] = vp;
-	if (HEAT) a.ou[o] = vu;
-	if (k == 0 && a.pr.lo_p) { a.pr.lo_p[col] = vp; if (HEAT) a.pr.lo_u[col] = vu; }
-	if (k == n3 - 1 && a.pr.hi_p) { a.pr.hi_p[col] = vp; if (HEAT) a.pr.hi_u[col] = vu; }
+	w.op[o] = vp;
+	if (HEAT) w.ou[o] = vu;
+	if (k == 0 && w.lo_p) { w.lo_p[col] = vp; if (HEAT) w.lo_u[col] = vu; }
+	if (k == n3 - 1 && w.hi_p) { w.hi_p[col] = vp; if (HEAT) w.hi_u[col] = vu; }
 }
 
-// ---- stage 5 epilogue: grid-wide max of the error estimate, acceptance decision, host notification.
+// ---- stage 5 epilogue: grid-wide max of the error estimate, then the step decision.
 // Several GPUs: the last CTA of every rank's launch hands its slab maximum to every rank (peer stores,
 // one thread per rank), waits for the others' and forms the global maximum -- the role of
 // MPI_Allreduce(MAX), RK_MPI_SAsolver_hybrid2.c:572 -- so that every rank takes the same decision
 // without a further launch.  Peers never wait for THIS CTA (their boundary waits concern CTAs that
 // are long finished), so the spin cannot deadlock.
+// The decision itself (pft_ctl.h: accept test, new step length with the host library's pow, update of
+// t / h / which pair holds x, end-of-interval logic, derived scalars of the next attempt) is taken by
+// ONE thread here; the next launches read its result from the control block.
 __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, double emax, int nonfinite)
 {
 	// CTA max through a shared-memory atomic on the bit pattern (non-negative doubles order
@@ -360,8 +386,8 @@ __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, doubl
 	if (emax > 0.0) atomicMax(&s_bits, (unsigned long long)__double_as_longlong(emax));
 	if (nonfinite) atomicOr(&s_nonfinite, 1);
 	__syncthreads();
+	StepCtl *ctl = a.ctl;
 	if (tid == 0) {
-		Ctl *ctl = a.ctl;
 		if (s_bits) atomicMax(&ctl->eps_bits, s_bits);
 		if (s_nonfinite) atomicOr(&ctl->nonfinite, 1);
 		__threadfence();
@@ -379,10 +405,10 @@ __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, doubl
 	__syncthreads();
 	if (!s_last) return;                     // CTA-uniform
 
+	const unsigned long long seq = ctl->aseq + 1ull;      // number of this attempt
 	if (a.pr.nranks > 1) {
-		const int b = (int)(a.seq & 1ull);
+		const int b = (int)(seq & 1ull);
 		const int nthr = blockDim.x * blockDim.y;
-		if (tid == 0) PFT_TRACE_MAX(a, 8, gtime());
 		const double mine = __longlong_as_double((long long)s_bits);
 		const int mine_nf = s_nonfinite;
 		__syncthreads();                     // everyone has read the slab result before it is overwritten below
@@ -391,13 +417,13 @@ __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, doubl
 			e->eps = mine;
 			e->nonfinite = mine_nf;
 			__threadfence_system();
-			st_release_sys(&e->seq, a.seq);
+			st_release_sys(&e->seq, seq);
 		}
 		if (tid == 0) { s_bits = 0ull; s_nonfinite = 0; }
 		__syncthreads();
 		for (int r = tid; r < a.pr.nranks; r += nthr) {
 			const EpsSlot *e = &a.pr.ranks[a.pr.rank]->slot[b][r];
-			while (ld_acquire_sys(&e->seq) != a.seq) { }
+			while (ld_acquire_sys(&e->seq) != seq) { }
 			const double v = *(volatile const double *)&e->eps;
 			if (v > 0.0) atomicMax(&s_bits, (unsigned long long)__double_as_longlong(v));
 			if (*(volatile const int *)&e->nonfinite) atomicOr(&s_nonfinite, 1);
@@ -407,25 +433,59 @@ __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, doubl
 	if (tid == 0) {
 		const double eps = __longlong_as_double((long long)s_bits);
 		const int nfl = s_nonfinite;
-		const double ecmp = a.scale_eps ? eps * a.eps_scale : eps;        // RK_MPI_SAsolver_hybrid2.c:578
-		int acc = (ecmp < a.delta) || (a.h_abs < a.h_min);                 // :599
-		if (a.handle_nan && nfl) acc = 0;                                   // :626-646
-		a.ctl->accept = acc;
-		__threadfence();
 		HostSlot *s = a.slot;
-		s->eps = eps;
-		s->accept = acc;
-		s->nonfinite = nfl;
-		__threadfence_system();
-		*(volatile unsigned long long *)&s->seq = a.seq;
-		PFT_TRACE_MAX(a, 9, gtime());
+		if (a.fin_mode == FIN_STORE_LOCAL) {
+			ctl->red[0] = eps; ctl->red[1] = nfl ? 1.0 : 0.0;
+		} else if (a.fin_mode == FIN_PUBLISH_EPS) {
+			ctl->red[0] = eps; ctl->red[1] = nfl ? 1.0 : 0.0;
+			s->eps = eps; s->nonfinite = nfl;
+			s->delta_local = ctl->delta_local; s->h3_attempt = fabs(ctl->h3);
+			__threadfence_system();
+			*(volatile unsigned long long *)&s->seq_eps = seq;
+		} else {
+			const double h_attempt = ctl->h;
+			const int cmd = ctl_decide(*ctl, eps, nfl, a.tab, 0.0);
+			__threadfence();
+			ctl_publish(*ctl, s, eps, nfl, cmd, h_attempt);
+			__threadfence_system();
+			*(volatile unsigned long long *)&s->seq = seq;
+		}
 	}
+}
+
+// the decision as a kernel of its own (one thread): after an NCCL all-reduce of StepCtl.red, and/or with
+// pow(delta/max_eps, 0.2) supplied by the host (use_host_pow)
+__global__ void ctl_decide_kernel(StepCtl *ctl, HostSlot *s, const PowTables *tab, double pw_host, int use_host_pow)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	if (ctl->status != ST_RUNNING) return;
+	const double eps = ctl->red[0];
+	const int nfl = ctl->red[1] != 0.0;
+	const unsigned long long seq = ctl->aseq + 1ull;
+	const double h_attempt = ctl->h;
+	const int cmd = ctl_decide(*ctl, eps, nfl, use_host_pow ? nullptr : tab, pw_host);
+	__threadfence();
+	ctl_publish(*ctl, s, eps, nfl, cmd, h_attempt);
+	__threadfence_system();
+	*(volatile unsigned long long *)&s->seq = seq;
+}
+
+// NCCL path without a usable device pow: hand the all-reduced error maximum to the host
+__global__ void ctl_publish_eps_kernel(StepCtl *ctl, HostSlot *s)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	if (ctl->status != ST_RUNNING) return;
+	s->eps = ctl->red[0]; s->nonfinite = ctl->red[1] != 0.0;
+	s->delta_local = ctl->delta_local; s->h3_attempt = fabs(ctl->h3);
+	__threadfence_system();
+	*(volatile unsigned long long *)&s->seq_eps = ctl->aseq + 1ull;
 }
 
 // MODEL: 0 GradP (calc_mode 0/10), 1 SigmaP1-P (1/11), 2 temperature model (2)
 // HEAT : the heat equation is active (false for calc_mode 10/11: du/dt = 0, u is static)
-// SHARE: each cell computes its three '+' face fluxes and takes the '-' ones from its neighbours
-template <int STAGE, int MODEL, bool HEAT, bool SHARE>
+// Register-staged predecessor of merson_stage_tma (per-thread global loads, halo-duty threads); it serves
+// calc_mode 10/11 and, behind PFT_FLAG_LEGACY_LOADS, as an A/B reference for the TMA kernels.
+template <int STAGE, int MODEL, bool HEAT>
 __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ KParams P)
 {
 	const Consts &c = P.c;
@@ -434,10 +494,14 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 
 	pdl_launch();
 	pdl_wait();
-	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) { halo_skip(a.pr); return; } }
+	StageScalars sc;
+	if (!stage_begin<STAGE>(a, sc)) return;
+	if (STAGE == 1 && !a.standalone && ctl_ld(&a.ctl->skip1)) { halo_skip(a.pr, sc.hseq); return; }
+	const double *xu_ = a.xu[sc.cur], *xp_ = a.xp[sc.cur];
+	const OutPtrs w = out_ptrs<STAGE>(a, sc.cur);
+	const double ha = sc.ha, hb = sc.hb;
 
 	constexpr int NF = HEAT ? 3 : 1;        // fields kept in the shared tile: p [, u, gl]
-	constexpr bool FLUX = HEAT && SHARE;
 
 	const int TX = blockDim.x, TY = blockDim.y;
 	const int tx = threadIdx.x, ty = threadIdx.y;
@@ -447,8 +511,6 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 
 	PFT_DYN_SMEM(double, smem);
 	double *tile = smem;                                    // [2][NF][TS]
-	double *fxs = smem + 2 * NF * TS;                       // [TY][TX+1]  (FLUX)
-	double *fys = fxs + (FLUX ? TY * (TX + 1) : 0);         // [TY+1][TX]  (FLUX)
 
 	const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
 	const int i = i0 + tx, j = j0 + ty;
@@ -459,7 +521,7 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 	const int k0 = chunk_of_block(a.pr.nzc) * g.zc;
 	const int k1 = min(g.n3, k0 + g.zc);
 	const bool chunk_lo = (k0 == 0), chunk_hi = (k1 == g.n3);
-	halo_wait(a.pr, chunk_lo, chunk_hi, ty * blockDim.x + tx);
+	halo_wait(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);
 
 	// halo-ring duty: the first 2*TX+2*TY threads each fetch one ring cell per plane
 	const int nh = 2 * TX + 2 * TY;
@@ -478,9 +540,6 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 	}
 	const int cs = (ty + 1) * SP + (tx + 1);  // this thread's own slot
 
-	// face duty (FLUX): the tile's west and south boundary faces
-	const bool fduty = FLUX && tid < TX + TY;
-
 	Raw<STAGE, HEAT> rc = {}, rn = {}, rdummy = {};
 	double um, pm, gm;       // plane k-1
 	double uc, pc, gc;       // plane k
@@ -492,11 +551,11 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 	// ---- prologue: planes k0-1 (registers) and k0 (registers + tile 0)
 	{
 		const long long base = (long long)(k0 + 1) * g.plane;
-		load_state<STAGE, HEAT, true>(a, base + col, uc, pc, rc);
+		load_state<STAGE, HEAT, true>(a, xu_, xp_, ha, base + col, uc, pc, rc);
 		gc = a.gl[base + col];
 		if (k0 == 0 && g.front) { um = uc; pm = pc; gm = gc; }          // z-front mirror (equation.c:164-174)
 		else {
-			load_state<STAGE, HEAT, false>(a, base - g.plane + col, um, pm, rdummy);
+			load_state<STAGE, HEAT, false>(a, xu_, xp_, ha, base - g.plane + col, um, pm, rdummy);
 			gm = a.gl[base - g.plane + col];
 		}
 		double *t0 = tile;
@@ -504,7 +563,7 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 		if (HEAT) { t0[TS + cs] = uc; t0[2 * TS + cs] = gc; }
 		if (hduty) {
 			double hu, hp;
-			load_state<STAGE, HEAT, false>(a, base + hcol, hu, hp, rdummy);
+			load_state<STAGE, HEAT, false>(a, xu_, xp_, ha, base + hcol, hu, hp, rdummy);
 			t0[hs] = hp;
 			if (HEAT) { t0[TS + hs] = hu; t0[2 * TS + hs] = a.gl[base + hcol]; }
 		}
@@ -520,13 +579,13 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 		// ---- fetch plane k+1 (kept in registers until the end of the iteration)
 		double hu = 0.0, hp = 0.0, hg = 0.0;
 		if (top) {
-			un = a.dir_u; pn = pc; gn = gc;                           // equation.c:175-183 / :251-261
+			un = sc.dir_u; pn = pc; gn = gc;                          // equation.c:175-183 / :251-261
 		} else {
-			load_state<STAGE, HEAT, true>(a, base_n + col, un, pn, rn);
+			load_state<STAGE, HEAT, true>(a, xu_, xp_, ha, base_n + col, un, pn, rn);
 			gn = a.gl[base_n + col];
 		}
 		if (more && hduty) {
-			load_state<STAGE, HEAT, false>(a, base_n + hcol, hu, hp, rdummy);
+			load_state<STAGE, HEAT, false>(a, xu_, xp_, ha, base_n + hcol, hu, hp, rdummy);
 			if (HEAT) hg = a.gl[base_n + hcol];
 		}
 
@@ -540,30 +599,12 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 		if (HEAT) {
 			const double ue = tu[cs + 1], ge = tg[cs + 1];
 			const double unn = tu[cs + SP], gnn = tg[cs + SP];
+			const double uw = tu[cs - 1], gw = tg[cs - 1];
+			const double us = tu[cs - SP], gs = tg[cs - SP];
 			double fe = face_flux(c, pc, pe, gc, ge, uc, ue);
 			double fn = face_flux(c, pc, pnn, gc, gnn, uc, unn);
-			double fw, fs;
-			if (FLUX) {
-				fxs[ty * (TX + 1) + tx + 1] = fe;
-				fys[(ty + 1) * TX + tx] = fn;
-				if (fduty) {
-					if (tid < TY) {          // west boundary face of row `tid`
-						int s0 = (tid + 1) * SP;
-						fxs[tid * (TX + 1)] = face_flux(c, tp[s0], tp[s0 + 1], tg[s0], tg[s0 + 1], tu[s0], tu[s0 + 1]);
-					} else {                 // south boundary face of column `tid-TY`
-						int s0 = (tid - TY) + 1;
-						fys[tid - TY] = face_flux(c, tp[s0], tp[s0 + SP], tg[s0], tg[s0 + SP], tu[s0], tu[s0 + SP]);
-					}
-				}
-				__syncthreads();
-				fw = fxs[ty * (TX + 1) + tx];
-				fs = fys[ty * TX + tx];
-			} else {
-				const double uw = tu[cs - 1], gw = tg[cs - 1];
-				const double us = tu[cs - SP], gs = tg[cs - SP];
-				fw = face_flux(c, pw, pc, gw, gc, uw, uc);
-				fs = face_flux(c, ps, pc, gs, gc, us, uc);
-			}
+			double fw = face_flux(c, pw, pc, gw, gc, uw, uc);
+			double fs = face_flux(c, ps, pc, gs, gc, us, uc);
 			// the z+ face is the first consumer of the plane fetched at the top of this iteration:
 			// keep it last so that the in-plane work covers the load latency
 			double fzp = face_flux(c, pc, pn, gc, gn, uc, un);
@@ -608,24 +649,24 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 		if (active) {
 			const long long o = (long long)(k + 1) * g.plane + col;
 			if (STAGE == 1 || STAGE == 3 || STAGE == 4) {
-				store_out<HEAT>(a, o, col, k, g.n3, du, dp);
+				store_out<HEAT>(w, o, col, k, g.n3, du, dp);
 			} else if (STAGE == 2) {
-				const double vp = (rc.k1p + dp) * a.hb + rc.xp;                               // :408
-				const double vu = HEAT ? (rc.k1u + du) * a.hb + rc.xu : 0.0;
-				store_out<HEAT>(a, o, col, k, g.n3, vu, vp);
+				const double vp = (rc.k1p + dp) * hb + rc.xp;                                 // :408
+				const double vu = HEAT ? (rc.k1u + du) * hb + rc.xu : 0.0;
+				store_out<HEAT>(w, o, col, k, g.n3, vu, vp);
 			} else {
 				double e = fabs(0.2 * rc.k1p - 0.9 * rc.k3p + 0.8 * rc.k4p - 0.1 * dp);   // :521
 				if (!(e <= 1.7976931348623157e308)) nonfinite = 1;
 				emax = (e > emax) ? e : emax;
-				const double vp = rc.xp + a.hb * (0.5 * (rc.k1p + dp) + 2.0 * rc.k4p);        // :667
+				const double vp = rc.xp + hb * (0.5 * (rc.k1p + dp) + 2.0 * rc.k4p);          // :667
 				double vu = 0.0;
 				if (HEAT) {
 					double eu = fabs(0.2 * rc.k1u - 0.9 * rc.k3u + 0.8 * rc.k4u - 0.1 * du);
 					if (!(eu <= 1.7976931348623157e308)) nonfinite = 1;
 					emax = (eu > emax) ? eu : emax;
-					vu = rc.xu + a.hb * (0.5 * (rc.k1u + du) + 2.0 * rc.k4u);
+					vu = rc.xu + hb * (0.5 * (rc.k1u + du) + 2.0 * rc.k4u);
 				}
-				store_out<HEAT>(a, o, col, k, g.n3, vu, vp);
+				store_out<HEAT>(w, o, col, k, g.n3, vu, vp);
 			}
 		}
 
@@ -645,7 +686,7 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 		cur ^= 1;
 	}
 
-	halo_signal(a.pr, chunk_lo, chunk_hi, tid);
+	halo_signal(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
 }
 
@@ -653,16 +694,17 @@ __global__ void __launch_bounds__(512, 1) merson_stage(const __grid_constant__ K
 // layout conversion between the reference's padded host layout (staged in device memory) and the
 // compact device layout
 
-// dir 0: padded -> compact (interior only), dir 1: compact -> padded (interior only)
-__global__ void repack_kernel(double *padded, double *compact, int n1, int n2, int n3, int px, long long plane,
+// dir 0: padded -> compact, dir 1: compact -> padded; planes klo .. khi-1 of the slab (interior: 0 .. n3-1;
+// klo = -1 / khi = n3+1 include the z-ghost plane of BOTH layouts: a neighbouring slab's boundary plane)
+__global__ void repack_kernel(double *padded, double *compact, int n1, int n2, int klo, int khi, int px, long long plane,
                               int N1, long long rowsize, int bt, int dir)
 {
-	const long long total = (long long)n1 * n2 * n3;
+	const long long total = (long long)n1 * n2 * (khi - klo);
 	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
 		int i = (int)(t % n1);
 		long long r = t / n1;
 		int j = (int)(r % n2);
-		int k = (int)(r / n2);
+		int k = (int)(r / n2) + klo;
 		long long ip = (long long)(k + bt) * rowsize + (long long)(j + bt) * N1 + bt + i;
 		long long ic = (long long)(k + 1) * plane + (long long)j * px + i;
 		if (dir == 0) compact[ic] = padded[ip];
@@ -685,44 +727,63 @@ __global__ void dense_kernel(double *dense, double *compact, int n1, int n2, int
 	}
 }
 
-// sphere rasteriser (equation.c:508-529): gl = max(gl, 0.5*(1 - tanh(0.5/xi_gl*(|x-c| + 1e-10 - R))))
-__global__ void rasterise_kernel(double *gl, const double *bx, const double *by, const double *bz, int count,
+// uniform bins over the slab's bounding box, edge >= the culling radius (host side: pft_rasterise)
+struct RasterBins {
+	double org[3], inv[3];
+	int nb[3];
+};
+
+// sphere rasteriser (equation.c:508-529): gl = max(gl, 0.5*(1 - tanh(0.5/xi_gl*(|x-c| + 1e-10 - R)))).
+// tanh(a) rounds to exactly 1.0 for a > 19.07, i.e. the profile of a sphere further away than
+// cut = R + 19.5/s is exactly 0 and cannot raise gl >= 0.  The centres are sorted into bins of edge >= cut
+// (start[b] .. start[b+1]), so a node visits the 27 bins around it: every sphere within `cut` of the node is
+// among them, the others would not have changed the result -- bit-identical to testing every sphere, and
+// max() does not care about the order.
+__global__ void rasterise_kernel(double *gl, const double *centres, const int *start, const RasterBins rb,
                                  int n1, int n2, int n3, int px, long long plane, int first_row, int total_n3,
                                  double L1, double L2, double L3, double xi_gl, double radius)
 {
-	PFT_DYN_SMEM(double, sb);           // staged sphere centres, `chunk` at a time
-	const int chunk = blockDim.x;
 	const long long total = (long long)n1 * n2 * n3;
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const bool valid = t < total;
-	int i = 0, j = 0, k = 0;
-	if (valid) { i = (int)(t % n1); long long r = t / n1; j = (int)(r % n2); k = (int)(r / n2); }
+	if (t >= total) return;
+	const int i = (int)(t % n1);
+	const long long r = t / n1;
+	const int j = (int)(r % n2), k = (int)(r / n2);
 	const double x = L1 * (0.5 + i) / n1;
 	const double y = L2 * (0.5 + j) / n2;
 	const double z = L3 * (0.5 + k + first_row) / total_n3;
 	const long long ic = (long long)(k + 1) * plane + (long long)j * px + i;
-	double v = valid ? gl[ic] : 0.0;
+	double v = gl[ic];
 	const double s = 0.5 / xi_gl;
-	// tanh(a) rounds to exactly 1.0 for a > 19.07, i.e. the profile of a sphere further away than
-	// R + 19.5/s is exactly 0 and cannot raise gl >= 0: skip its sqrt/tanh (result-neutral, bit for bit)
 	const double cut = radius + 19.5 / s;
 	const double cut2 = cut * cut;
-	for (int q0 = 0; q0 < count; q0 += chunk) {
-		int q = q0 + threadIdx.x;
-		__syncthreads();
-		if (q < count) { sb[threadIdx.x] = bx[q]; sb[chunk + threadIdx.x] = by[q]; sb[2 * chunk + threadIdx.x] = bz[q]; }
-		__syncthreads();
-		int m = min(chunk, count - q0);
-		for (int qq = 0; qq < m; ++qq) {
-			double dx = x - sb[qq], dy = y - sb[chunk + qq], dz = z - sb[2 * chunk + qq];
-			double d2 = dx * dx + dy * dy + dz * dz;
-			if (d2 > cut2) continue;
-			double d = sqrt(d2) + 1E-10;
-			double f = 0.5 * (1.0 - tanh(s * (d - radius)));
-			v = (v < f) ? f : v;
-		}
+	const double pos[3] = {x, y, z};
+	int b0[3], b1[3];
+	for (int d = 0; d < 3; d++) {
+		const double f = (pos[d] - rb.org[d]) * rb.inv[d];
+		const int c = (f < 0) ? 0 : (f >= rb.nb[d] ? rb.nb[d] - 1 : (int)f);
+		b0[d] = max(c - 1, 0); b1[d] = min(c + 1, rb.nb[d] - 1);
 	}
-	if (valid) gl[ic] = v;
+	for (int bz = b0[2]; bz <= b1[2]; bz++)
+		for (int by = b0[1]; by <= b1[1]; by++) {
+			const int row = (bz * rb.nb[1] + by) * rb.nb[0];
+			const int q0 = start[row + b0[0]], q1 = start[row + b1[0] + 1];      // the x-neighbour bins are contiguous
+			for (int q = q0; q < q1; q++) {
+				const double dx = x - centres[3 * q], dy = y - centres[3 * q + 1], dz = z - centres[3 * q + 2];
+				const double d2 = dx * dx + dy * dy + dz * dz;
+				if (d2 > cut2) continue;
+				const double d = sqrt(d2) + 1E-10;
+				const double f = 0.5 * (1.0 - tanh(s * (d - radius)));
+				v = (v < f) ? f : v;
+			}
+		}
+	gl[ic] = v;
+}
+
+// test hook: the device instance of the controller's pow twin on an array (pft_debug_pow)
+__global__ void pow_twin_kernel(const PowTables *tab, const double *x, double y, double *out, int n)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = pft_pow_twin(*tab, x[i], y);
 }
 
 // count of interior nodes with p > 0.5 (scripts/avg.sh:9-20)

@@ -36,7 +36,8 @@ constexpr int TMA_MAX_ARRAYS = 9;
 constexpr int TMA_STAGES = 3;
 
 struct alignas(64) TmaParams {
-	CUtensorMap maps[TMA_MAX_ARRAYS];   // order: p-type arrays, u-type arrays, gl (see stage_np)
+	CUtensorMap maps[TMA_MAX_ARRAYS];   // order: p-type arrays, u-type arrays, gl (see stage_np); x = pair A_X
+	CUtensorMap xalt[2];                 // the other state pair (A_XN): p, u -- used when StepCtl.cur == 1
 	Consts c;
 	Geom g;
 	StageArgs a;
@@ -156,14 +157,14 @@ __device__ __forceinline__ void cell_rhs(const Consts &c, double uc, double pc, 
 
 // the fused combination that follows stage STAGE, for one cell (operands from the raw buffer)
 template <int STAGE>
-__device__ __forceinline__ void stage_output(const StageArgs &a, const double *rb, int AS, int IU, int cs, long long o,
+__device__ __forceinline__ void stage_output(const OutPtrs &a, double hb, const double *rb, int AS, int IU, int cs, long long o,
                                              long long col, int k, int n3, double du, double dp, double &emax, int &nonfinite)
 {
 	if (STAGE == 1 || STAGE == 3 || STAGE == 4) {
 		store_out<true>(a, o, col, k, n3, du, dp);
 	} else if (STAGE == 2) {
-		const double vp = (rb[AS + cs] + dp) * a.hb + rb[cs];                                   // hybrid2.c:408
-		const double vu = (rb[(IU + 1) * AS + cs] + du) * a.hb + rb[IU * AS + cs];
+		const double vp = (rb[AS + cs] + dp) * hb + rb[cs];                                     // hybrid2.c:408
+		const double vu = (rb[(IU + 1) * AS + cs] + du) * hb + rb[IU * AS + cs];
 		store_out<true>(a, o, col, k, n3, vu, vp);
 	} else {
 		const double xp = rb[cs], k1p = rb[AS + cs], k3p = rb[2 * AS + cs], k4p = rb[3 * AS + cs];
@@ -173,23 +174,14 @@ __device__ __forceinline__ void stage_output(const StageArgs &a, const double *r
 		if (!(e <= 1.7976931348623157e308) || !(eu <= 1.7976931348623157e308)) nonfinite = 1;
 		emax = (e > emax) ? e : emax;
 		emax = (eu > emax) ? eu : emax;
-		const double vp = xp + a.hb * (0.5 * (k1p + dp) + 2.0 * k4p);                           // :667
-		const double vu = xu + a.hb * (0.5 * (k1u + du) + 2.0 * k4u);
+		const double vp = xp + hb * (0.5 * (k1p + dp) + 2.0 * k4p);                           // :667
+		const double vu = xu + hb * (0.5 * (k1u + du) + 2.0 * k4u);
 		store_out<true>(a, o, col, k, n3, vu, vp);
 	}
 }
 
-// one lane per warp arrives for the whole warp (the mbarrier is initialised with the warp count)
-__device__ __forceinline__ void warp_arrive(uint64_t *bar, int lane)
-{
-	__syncwarp();
-	if (lane == 0) mbar_arrive(bar);
-}
-
-// SPLIT: replace the CTA barrier that ends a plane by split-phase mbarriers (arrive now, wait one or
-// two planes later), so that warps may drift up to a plane apart instead of idling at a barrier
-template <int STAGE, int MODEL, bool SHARE, bool SPLIT>
-__global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_stage_tma(const __grid_constant__ TmaParams P)
+template <int STAGE, int MODEL>
+__global__ void __launch_bounds__(256, (STAGE == 5) ? 2 : 3) merson_stage_tma(const __grid_constant__ TmaParams P)
 {
 	const Consts &c = P.c;
 	const Geom &g = P.g;
@@ -201,22 +193,16 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 	constexpr int NA = 2 * NP + 1;
 	constexpr bool FORM = !(STAGE == 1 || STAGE == 3);
 	constexpr int IU = NP, IG = 2 * NP;          // first u-type array, the gl array
-	constexpr int NT = FORM ? (SPLIT ? 3 : 2) : 0;   // state tile buffers
 
 	const int TX = blockDim.x, TY = blockDim.y;
 	const int tx = threadIdx.x, ty = threadIdx.y;
 	const int tid = ty * TX + tx;
-	const int lane = tid & 31;
 	const int BX = P.bx, AS = P.as;
 
 	PFT_DYN_SMEM_ALIGNED(double, smem_t);
 	double *raw = smem_t;                                            // [3][NA][AS]
-	double *tile = raw + TMA_STAGES * NA * AS;                       // [NT][2][AS]  (FORM)
-	double *fxs = tile + NT * 2 * AS;                                // [TY][TX+1]   (SHARE)
-	double *fys = fxs + (SHARE ? TY * (TX + 1) : 0);                 // [TY+1][TX]   (SHARE)
+	double *tile = raw + TMA_STAGES * NA * AS;                       // [2][2][AS]  (FORM)
 	__shared__ uint64_t full[TMA_STAGES];    // raw plane landed (TMA complete_tx)
-	__shared__ uint64_t tready[3];           // SPLIT: state tile formed by every warp
-	__shared__ uint64_t done[2];             // SPLIT: every warp finished a plane (even / odd planes)
 
 	const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
 	const int i = i0 + tx, j = j0 + ty;
@@ -246,38 +232,33 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 		else { hx = TX; hy = tid - 2 * TX - TY; }
 		hs = (hy + 1) * BX + (hx + 2);
 	}
-	const bool fduty = SHARE && tid < TX + TY;
 
 	if (tid == 0) {
-		const int nwarps = (TX * TY + 31) >> 5;
-		for (int b = 0; b < TMA_STAGES; b++) { mbar_init(&full[b], 1); mbar_init(&tready[b], nwarps); }
-		mbar_init(&done[0], nwarps); mbar_init(&done[1], nwarps);
+		for (int b = 0; b < TMA_STAGES; b++) mbar_init(&full[b], 1);
 		fence_mbar_init();
 	}
 	__syncthreads();
 	pdl_wait();                                   // from here on this launch reads what its predecessor wrote
-	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) { halo_skip(a.pr); return; } }
-#ifdef PFT_TRACE
-	unsigned long long tr_t0 = 0;
-	if (tid == 0) { tr_t0 = gtime(); PFT_TRACE_MAX(a, 0, ~tr_t0); PFT_TRACE_MAX(a, 1, tr_t0); }
-#endif
-	halo_wait(a.pr, chunk_lo, chunk_hi, tid);     // peer path: the neighbours' planes of the previous launch have landed
-#ifdef PFT_TRACE
-	if (tid == 0 && (chunk_lo || chunk_hi)) {
-		const unsigned long long t1 = gtime();
-		if (chunk_lo) PFT_TRACE_MAX(a, 3, t1);
-		if (chunk_hi) PFT_TRACE_MAX(a, 4, t1);
-		PFT_TRACE_MAX(a, 5, t1 - tr_t0);
-	}
-#endif
+	StageScalars sc;
+	if (!stage_begin<STAGE>(a, sc)) return;
+	if (STAGE == 1 && !a.standalone && ctl_ld(&a.ctl->skip1)) { halo_skip(a.pr, sc.hseq); return; }
+	const OutPtrs w = out_ptrs<STAGE>(a, sc.cur);
+	const double ha = sc.ha;
+	halo_wait(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);     // peer path: the neighbours' planes of the previous launch have landed
 
-	// thread 0 requests plane q into raw buffer b: one tensor copy per array
+	// thread 0 requests plane q into raw buffer b: one tensor copy per array.  The state pair x is
+	// array 0 (p) and array IU (u) of every stage but the third; which pair holds x is StepCtl.cur.
 	const uint32_t plane_bytes = (uint32_t)(NA * BX * P.by * sizeof(double));
+	const bool alt = (STAGE != 3) && sc.cur != 0;
 	auto issue = [&](int q, int b) {
 		mbar_arrive_expect_tx(&full[b], plane_bytes);
 		#pragma unroll
-		for (int m = 0; m < NA; m++)
-			tma_load_3d(raw + (b * NA + m) * AS, &P.maps[m], i0 - 2, j0 - 1, k0 + q, &full[b]);
+		for (int m = 0; m < NA; m++) {
+			const CUtensorMap *map = &P.maps[m];
+			if (alt && m == 0) map = &P.xalt[0];
+			if (alt && m == IU) map = &P.xalt[1];
+			tma_load_3d(raw + (b * NA + m) * AS, map, i0 - 2, j0 - 1, k0 + q, &full[b]);
+		}
 	};
 	int next_q = qlo;
 	if (tid == 0) {
@@ -285,7 +266,7 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 		for (int n = 0; n < TMA_STAGES && next_q <= qhi; n++, next_q++) issue(next_q, next_q % TMA_STAGES);
 	}
 
-	uint32_t full_bits = 0, tile_bits = 0;       // parity of the next completion to wait for, per buffer
+	uint32_t full_bits = 0;                      // parity of the next completion to wait for, per buffer
 	double um, pm, gm, uc, pc, gc, un, pn, gn;
 	double fzm = 0.0, emax = 0.0;
 	int nonfinite = 0;
@@ -293,19 +274,19 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 	// ---- prologue: planes k0-1 (registers only) and k0 (registers + tile 0)
 	if (qlo == 0) {
 		mbar_wait(&full[0], 0); full_bits ^= 1u;
-		pm = form_state<STAGE>(raw, AS, cs, 0, a.ha);
-		um = form_state<STAGE>(raw, AS, cs, IU, a.ha);
+		pm = form_state<STAGE>(raw, AS, cs, 0, ha);
+		um = form_state<STAGE>(raw, AS, cs, IU, ha);
 		gm = raw[IG * AS + cs];
 	}
 	{
 		mbar_wait(&full[1], 0); full_bits ^= 2u;
 		const double *rb = raw + NA * AS;
-		pc = form_state<STAGE>(rb, AS, cs, 0, a.ha);
-		uc = form_state<STAGE>(rb, AS, cs, IU, a.ha);
+		pc = form_state<STAGE>(rb, AS, cs, 0, ha);
+		uc = form_state<STAGE>(rb, AS, cs, IU, ha);
 		gc = rb[IG * AS + cs];
 		if (FORM) {
 			tile[cs] = pc; tile[AS + cs] = uc;
-			if (hduty) { tile[hs] = form_state<STAGE>(rb, AS, hs, 0, a.ha); tile[AS + hs] = form_state<STAGE>(rb, AS, hs, IU, a.ha); }
+			if (hduty) { tile[hs] = form_state<STAGE>(rb, AS, hs, 0, ha); tile[AS + hs] = form_state<STAGE>(rb, AS, hs, IU, ha); }
 		}
 		if (qlo == 1) { um = uc; pm = pc; gm = gc; }                  // equation.c:164-174
 		fzm = face_flux(c, pm, pc, gm, gc, um, uc);
@@ -322,36 +303,28 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 
 		// ---- thread 0: request plane q+2 into the buffer plane q-1 just vacated
 		if (tid == 0 && next_q <= qhi && next_q <= q + 2) {
-			if (SPLIT && it >= 1) mbar_wait(&done[(it - 1) & 1], ((it - 1) >> 1) & 1);
 			issue(next_q, bf);
 			next_q++;
 		}
 
 		// ---- plane k+1: form the stage input (centre -> registers, centre + ring -> its state tile)
 		if (q + 1 <= qhi) {
-			// SPLIT: tile[tn] was last read while plane k-2 was computed
-			if (SPLIT && FORM && more && it >= 2) mbar_wait(&done[it & 1], ((it - 2) >> 1) & 1);
 			mbar_wait(&full[bn], (full_bits >> bn) & 1u);
 			full_bits ^= (1u << bn);
 			const double *rn = raw + bn * NA * AS;
-			pn = form_state<STAGE>(rn, AS, cs, 0, a.ha);
-			un = form_state<STAGE>(rn, AS, cs, IU, a.ha);
+			pn = form_state<STAGE>(rn, AS, cs, 0, ha);
+			un = form_state<STAGE>(rn, AS, cs, IU, ha);
 			gn = rn[IG * AS + cs];
 			if (FORM && more) {
 				double *tw = tile + tn * 2 * AS;
 				tw[cs] = pn; tw[AS + cs] = un;
-				if (hduty) { tw[hs] = form_state<STAGE>(rn, AS, hs, 0, a.ha); tw[AS + hs] = form_state<STAGE>(rn, AS, hs, IU, a.ha); }
-				if (SPLIT) warp_arrive(&tready[tn], lane);
+				if (hduty) { tw[hs] = form_state<STAGE>(rn, AS, hs, 0, ha); tw[AS + hs] = form_state<STAGE>(rn, AS, hs, IU, ha); }
 			}
 		} else {
-			un = a.dir_u; pn = pc; gn = gc;                             // equation.c:175-183 / :251-261
+			un = sc.dir_u; pn = pc; gn = gc;                            // equation.c:175-183 / :251-261
 		}
 
 		// ---- plane k
-		if (SPLIT && FORM && it >= 1) {                                 // its tile was formed while plane k-1 was computed
-			mbar_wait(&tready[tc], (tile_bits >> tc) & 1u);
-			tile_bits ^= (1u << tc);
-		}
 		const double *tp = FORM ? tile + tc * 2 * AS : rb;
 		const double *tu = FORM ? tp + AS : rb + IU * AS;
 		const double pw = tp[sW], pe = tp[sE], ps = tp[sS], pnn = tp[sN];
@@ -362,29 +335,8 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 			const double unn = tu[sN], gnn = rg[sN];
 			double fe = face_flux(c, pc, pe, gc, ge, uc, ue);
 			double fn = face_flux(c, pc, pnn, gc, gnn, uc, unn);
-			double fw, fs;
-			if (SHARE) {
-				fxs[ty * (TX + 1) + tx + 1] = fe;
-				fys[(ty + 1) * TX + tx] = fn;
-				if (fduty) {
-					if (tid < TY) {           // west boundary face of tile row `tid`
-						const int s1 = (tid + 1) * BX + 2;
-						const int s0 = (i0 > 0) ? s1 - 1 : s1;
-						fxs[tid * (TX + 1)] = face_flux(c, tp[s0], tp[s1], rg[s0], rg[s1], tu[s0], tu[s1]);
-					} else {                  // south boundary face of tile column `tid-TY`
-						const int s1 = BX + (tid - TY) + 2;
-						const int s0 = (j0 > 0) ? s1 - BX : s1;
-						fys[tid - TY] = face_flux(c, tp[s0], tp[s1], rg[s0], rg[s1], tu[s0], tu[s1]);
-					}
-				}
-				__syncthreads();
-				fw = fxs[ty * (TX + 1) + tx];
-				fs = fys[ty * TX + tx];
-				__syncthreads();      // (SHARE is the A/B variant: keep it simple and safe)
-			} else {
-				fw = face_flux(c, pw, pc, rg[sW], gc, tu[sW], uc);
-				fs = face_flux(c, ps, pc, rg[sS], gc, tu[sS], uc);
-			}
+			double fw = face_flux(c, pw, pc, rg[sW], gc, tu[sW], uc);
+			double fs = face_flux(c, ps, pc, rg[sS], gc, tu[sS], uc);
 			double fzp = face_flux(c, pc, pn, gc, gn, uc, un);
 			sum = c.h1_2 * (-fw + fe) + c.h2_2 * (-fs + fn) + c.h3_2 * (-fzm + fzp);   // equation.c:711-720
 			fzm = fzp;
@@ -396,235 +348,18 @@ __global__ void __launch_bounds__(256, (STAGE == 5 || SHARE) ? 2 : 3) merson_sta
 		// ---- fused combination that follows this stage (operands re-read from the raw buffer)
 		if (active) {
 			const long long col = (long long)j * g.px + i;
-			stage_output<STAGE>(a, rb, AS, IU, cs, (long long)(k + 1) * g.plane + col, col, k, g.n3, du, dp, emax, nonfinite);
+			stage_output<STAGE>(w, sc.hb, rb, AS, IU, cs, (long long)(k + 1) * g.plane + col, col, k, g.n3, du, dp, emax, nonfinite);
 		}
 
 		// ---- this plane is done: raw[bq] may be refilled, tile[tc] overwritten (two planes later)
-		if (SPLIT) warp_arrive(&done[it & 1], lane);
-		else __syncthreads();
+		__syncthreads();
 		um = uc; pm = pc; gm = gc;
 		uc = un; pc = pn; gc = gn;
 		{ const int t = bq; bq = bn; bn = bf; bf = t; }
-		if (FORM) { tc = tn; tn = (tn + 1 == NT) ? 0 : tn + 1; }
+		if (FORM) { tc = tn; tn ^= 1; }
 	}
 
-#ifdef PFT_TRACE
-	unsigned long long tr_t1 = 0;
-	if (tid == 0) tr_t1 = gtime();
-#endif
-	halo_signal(a.pr, chunk_lo, chunk_hi, tid);
-#ifdef PFT_TRACE
-	if (tid == 0) {
-		const unsigned long long t2 = gtime();
-		if ((chunk_lo && a.pr.wait_lo) || (chunk_hi && a.pr.wait_hi)) PFT_TRACE_MAX(a, 10, t2 - tr_t1);   // longest halo_signal
-		PFT_TRACE_MAX(a, chunk_lo ? 11 : (chunk_hi ? 12 : 13), tr_t1 - tr_t0);                            // longest CTA body per chunk class
-		PFT_TRACE_MAX(a, 2, t2);
-		if (a.trace_cta) {
-			const unsigned int lb = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-			if (lb < 1024u) {
-				unsigned int smid;
-				asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-				unsigned long long *r = a.trace_cta + 4ull * lb;
-				r[0] = tr_t0; r[1] = tr_t1; r[2] = t2; r[3] = ((unsigned long long)smid << 32) | (unsigned int)(k0 / g.zc);
-			}
-		}
-		if (chunk_lo) PFT_TRACE_MAX(a, 6, t2);      // the last one to pass here is (about) when the flag went out
-		if (chunk_hi) PFT_TRACE_MAX(a, 7, t2);
-	}
-#endif
-	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
-}
-
-// ----------------------------------------------------------------------------------------
-// merson_stage_tma2: as merson_stage_tma, but every thread owns TWO vertically adjacent cells
-// (rows 2*ty and 2*ty+1 of a TX x 2*TY tile).  The face between them is computed once, the
-// address arithmetic, constant fetches and loop control are paid once per two cells, and the two
-// independent dependency chains double the instruction-level parallelism the fp64 pipe sees.
-
-template <int STAGE, int MODEL>
-__global__ void __launch_bounds__(256, 2) merson_stage_tma2(const __grid_constant__ TmaParams P)
-{
-	const Consts &c = P.c;
-	const Geom &g = P.g;
-	const StageArgs &a = P.a;
-
-	pdl_launch();
-	pdl_wait();
-	if (STAGE == 1) { if (a.cond != nullptr && *a.cond == 0) { halo_skip(a.pr); return; } }
-
-	constexpr int NP = stage_np(STAGE);
-	constexpr int NA = 2 * NP + 1;
-	constexpr bool FORM = !(STAGE == 1 || STAGE == 3);
-	constexpr int IU = NP, IG = 2 * NP;
-
-	const int TX = blockDim.x, TY = blockDim.y, RY = 2 * TY;       // tile = TX x RY cells
-	const int tx = threadIdx.x, ty = threadIdx.y;
-	const int tid = ty * TX + tx, nthr = TX * TY;
-	const int BX = P.bx, AS = P.as;
-
-	PFT_DYN_SMEM_ALIGNED(double, smem_t);
-	double *raw = smem_t;                                            // [3][NA][AS]
-	double *tile = raw + TMA_STAGES * NA * AS;                       // [2][2][AS]  (FORM)
-	__shared__ uint64_t full[TMA_STAGES];
-
-	const int i0 = blockIdx.x * TX, j0 = blockIdx.y * RY;
-	const int i = i0 + tx, jA = j0 + 2 * ty, jB = jA + 1;
-	const bool actA = (i < g.n1) && (jA < g.n2), actB = (i < g.n1) && (jB < g.n2);
-	const bool hasB = jB < g.n2;                                     // else A's upper neighbour is its own mirror
-	const int csA = (2 * ty + 1) * BX + (tx + 2), csB = csA + BX;
-	// in-plane neighbour slots, clamped to the DOMAIN (zero-Neumann mirror, equation.c:142-160)
-	const int dW = (i > 0) ? -1 : 0, dE = (i < g.n1 - 1) ? 1 : 0;
-	const int sS = (jA > 0) ? csA - BX : csA;                        // below A
-	const int sN = (jB < g.n2 - 1) ? csB + BX : csB;                 // above B
-
-	const int k0 = chunk_of_block(a.pr.nzc) * g.zc;
-	const int k1 = min(g.n3, k0 + g.zc);
-	const bool chunk_lo = (k0 == 0), chunk_hi = (k1 == g.n3);
-	const int qlo = (k0 == 0 && g.front) ? 1 : 0;
-	const int qhi = (k1 == g.n3 && g.rear) ? (k1 - k0) : (k1 - k0 + 1);
-
-	// ring duty (FORM): 2*TX + 2*RY ring cells, up to two per thread
-	int hs0 = -1, hs1 = -1;
-	if (FORM) {
-		const int nring = 2 * TX + 2 * RY;
-		#pragma unroll
-		for (int r = 0; r < 2; r++) {
-			const int h = tid + r * nthr;
-			int slot = -1;
-			if (h < nring) {
-				int hx, hy;
-				if (h < TX) { hx = h; hy = -1; }
-				else if (h < 2 * TX) { hx = h - TX; hy = RY; }
-				else if (h < 2 * TX + RY) { hx = -1; hy = h - 2 * TX; }
-				else { hx = TX; hy = h - 2 * TX - RY; }
-				slot = (hy + 1) * BX + (hx + 2);
-			}
-			if (r == 0) hs0 = slot; else hs1 = slot;
-		}
-	}
-
-	if (tid == 0) {
-		for (int b = 0; b < TMA_STAGES; b++) mbar_init(&full[b], 1);
-		fence_mbar_init();
-	}
-	__syncthreads();
-	halo_wait(a.pr, chunk_lo, chunk_hi, tid);     // peer path: the neighbours' planes of the previous launch have landed
-
-	const uint32_t plane_bytes = (uint32_t)(NA * BX * P.by * sizeof(double));
-	auto issue = [&](int q, int b) {
-		mbar_arrive_expect_tx(&full[b], plane_bytes);
-		#pragma unroll
-		for (int m = 0; m < NA; m++)
-			tma_load_3d(raw + (b * NA + m) * AS, &P.maps[m], i0 - 2, j0 - 1, k0 + q, &full[b]);
-	};
-	int next_q = qlo;
-	if (tid == 0) {
-		#pragma unroll 1
-		for (int n = 0; n < TMA_STAGES && next_q <= qhi; n++, next_q++) issue(next_q, next_q % TMA_STAGES);
-	}
-
-	uint32_t full_bits = 0;
-	double umA, pmA, gmA, ucA, pcA, gcA, unA, pnA, gnA;
-	double umB, pmB, gmB, ucB, pcB, gcB, unB, pnB, gnB;
-	double fzA = 0.0, fzB = 0.0, emax = 0.0;
-	int nonfinite = 0;
-
-	// ---- prologue
-	if (qlo == 0) {
-		mbar_wait(&full[0], 0); full_bits ^= 1u;
-		pmA = form_state<STAGE>(raw, AS, csA, 0, a.ha); umA = form_state<STAGE>(raw, AS, csA, IU, a.ha); gmA = raw[IG * AS + csA];
-		pmB = form_state<STAGE>(raw, AS, csB, 0, a.ha); umB = form_state<STAGE>(raw, AS, csB, IU, a.ha); gmB = raw[IG * AS + csB];
-	}
-	{
-		mbar_wait(&full[1], 0); full_bits ^= 2u;
-		const double *rb = raw + NA * AS;
-		pcA = form_state<STAGE>(rb, AS, csA, 0, a.ha); ucA = form_state<STAGE>(rb, AS, csA, IU, a.ha); gcA = rb[IG * AS + csA];
-		pcB = form_state<STAGE>(rb, AS, csB, 0, a.ha); ucB = form_state<STAGE>(rb, AS, csB, IU, a.ha); gcB = rb[IG * AS + csB];
-		if (FORM) {
-			tile[csA] = pcA; tile[AS + csA] = ucA; tile[csB] = pcB; tile[AS + csB] = ucB;
-			if (hs0 >= 0) { tile[hs0] = form_state<STAGE>(rb, AS, hs0, 0, a.ha); tile[AS + hs0] = form_state<STAGE>(rb, AS, hs0, IU, a.ha); }
-			if (hs1 >= 0) { tile[hs1] = form_state<STAGE>(rb, AS, hs1, 0, a.ha); tile[AS + hs1] = form_state<STAGE>(rb, AS, hs1, IU, a.ha); }
-		}
-		if (qlo == 1) { umA = ucA; pmA = pcA; gmA = gcA; umB = ucB; pmB = pcB; gmB = gcB; }   // equation.c:164-174
-		fzA = face_flux(c, pmA, pcA, gmA, gcA, umA, ucA);
-		fzB = face_flux(c, pmB, pcB, gmB, gcB, umB, ucB);
-	}
-	__syncthreads();
-
-	int bq = 1, bn = 2, bf = 0, cur = 0;
-	for (int it = 0, k = k0; k < k1; ++k, ++it) {
-		const int q = it + 1;
-		const bool more = (k + 1 < k1);
-		const double *rb = raw + bq * NA * AS;
-		const double *rg = rb + IG * AS;
-
-		if (tid == 0 && next_q <= qhi && next_q <= q + 2) { issue(next_q, bf); next_q++; }
-
-		// ---- plane k+1: stage input (centres -> registers, centres + ring -> the other tile)
-		if (q + 1 <= qhi) {
-			mbar_wait(&full[bn], (full_bits >> bn) & 1u);
-			full_bits ^= (1u << bn);
-			const double *rn = raw + bn * NA * AS;
-			pnA = form_state<STAGE>(rn, AS, csA, 0, a.ha); unA = form_state<STAGE>(rn, AS, csA, IU, a.ha); gnA = rn[IG * AS + csA];
-			pnB = form_state<STAGE>(rn, AS, csB, 0, a.ha); unB = form_state<STAGE>(rn, AS, csB, IU, a.ha); gnB = rn[IG * AS + csB];
-			if (FORM && more) {
-				double *tw = tile + (cur ^ 1) * 2 * AS;
-				tw[csA] = pnA; tw[AS + csA] = unA; tw[csB] = pnB; tw[AS + csB] = unB;
-				if (hs0 >= 0) { tw[hs0] = form_state<STAGE>(rn, AS, hs0, 0, a.ha); tw[AS + hs0] = form_state<STAGE>(rn, AS, hs0, IU, a.ha); }
-				if (hs1 >= 0) { tw[hs1] = form_state<STAGE>(rn, AS, hs1, 0, a.ha); tw[AS + hs1] = form_state<STAGE>(rn, AS, hs1, IU, a.ha); }
-			}
-		} else {
-			unA = a.dir_u; pnA = pcA; gnA = gcA;                        // equation.c:175-183 / :251-261
-			unB = a.dir_u; pnB = pcB; gnB = gcB;
-		}
-
-		// ---- plane k, cells A (lower) and B (upper)
-		const double *tp = FORM ? tile + cur * 2 * AS : rb;
-		const double *tu = FORM ? tp + AS : rb + IU * AS;
-		const double pwA = tp[csA + dW], peA = tp[csA + dE], psA = tp[sS];
-		const double pwB = tp[csB + dW], peB = tp[csB + dE], pnB_ = tp[sN];
-		const double uwA = tu[csA + dW], ueA = tu[csA + dE], usA = tu[sS];
-		const double uwB = tu[csB + dW], ueB = tu[csB + dE], unB_ = tu[sN];
-		const double gwA = rg[csA + dW], geA = rg[csA + dE], gsA = rg[sS];
-		const double gwB = rg[csB + dW], geB = rg[csB + dE], gnB_ = rg[sN];
-		// A's upper neighbour: B, or A itself when B lies outside the domain (mirror)
-		const double pUp = hasB ? pcB : pcA, uUp = hasB ? ucB : ucA, gUp = hasB ? gcB : gcA;
-
-		const double fAB = face_flux(c, pcA, pUp, gcA, gUp, ucA, uUp);
-		double sumA, sumB;
-		{
-			double fw = face_flux(c, pwA, pcA, gwA, gcA, uwA, ucA);
-			double fe = face_flux(c, pcA, peA, gcA, geA, ucA, ueA);
-			double fs = face_flux(c, psA, pcA, gsA, gcA, usA, ucA);
-			double fz = face_flux(c, pcA, pnA, gcA, gnA, ucA, unA);
-			sumA = c.h1_2 * (-fw + fe) + c.h2_2 * (-fs + fAB) + c.h3_2 * (-fzA + fz);          // equation.c:711-720
-			fzA = fz;
-		}
-		{
-			double fw = face_flux(c, pwB, pcB, gwB, gcB, uwB, ucB);
-			double fe = face_flux(c, pcB, peB, gcB, geB, ucB, ueB);
-			double fn = face_flux(c, pcB, pnB_, gcB, gnB_, ucB, unB_);
-			double fz = face_flux(c, pcB, pnB, gcB, gnB, ucB, unB);
-			sumB = c.h1_2 * (-fw + fe) + c.h2_2 * (-fAB + fn) + c.h3_2 * (-fzB + fz);
-			fzB = fz;
-		}
-		double duA, dpA, duB, dpB;
-		cell_rhs<MODEL>(c, ucA, pcA, gcA, pwA, peA, psA, pUp, pmA, pnA, sumA, duA, dpA);
-		cell_rhs<MODEL>(c, ucB, pcB, gcB, pwB, peB, pcA, pnB_, pmB, pnB, sumB, duB, dpB);
-
-		const long long colA = (long long)jA * g.px + i;
-		const long long oA = (long long)(k + 1) * g.plane + colA;
-		if (actA) stage_output<STAGE>(a, rb, AS, IU, csA, oA, colA, k, g.n3, duA, dpA, emax, nonfinite);
-		if (actB) stage_output<STAGE>(a, rb, AS, IU, csB, oA + g.px, colA + g.px, k, g.n3, duB, dpB, emax, nonfinite);
-
-		__syncthreads();
-		umA = ucA; pmA = pcA; gmA = gcA; ucA = unA; pcA = pnA; gcA = gnA;
-		umB = ucB; pmB = pcB; gmB = gcB; ucB = unB; pcB = pnB; gcB = gnB;
-		cur ^= 1;
-		{ const int t = bq; bq = bn; bn = bf; bf = t; }
-	}
-
-	halo_signal(a.pr, chunk_lo, chunk_hi, tid);
+	halo_signal(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
 }
 

@@ -20,11 +20,12 @@ from .cases import CaseSpec, partition
 BT = 2
 NVAR = 3
 
-FLAG_NO_FLUX_SHARING = 1
-FLAG_NO_SPECULATION = 2
+FLAG_NO_RUNAHEAD = 2
 FLAG_RECOMPUTE_K1 = 4
 FLAG_LEGACY_LOADS = 8
-FLAG_FLUX_SHARING = 16
+FLAG_HOST_POW = 32
+
+FIELD_U, FIELD_P, FIELD_GL, FIELD_ALL = 1, 2, 4, 7
 
 SOLVE_DONE, SOLVE_INTERRUPTED, SOLVE_BUDGET = 0, 1, 2
 
@@ -116,6 +117,14 @@ class SlabSolver:
         assert x_padded.size == NVAR * self.SIZE
         self._check(self.lib.pft_download(self._h, _ptr(x_padded)), "pft_download")
 
+    def upload_fields(self, x_padded: np.ndarray, mask: int):
+        assert x_padded.size == NVAR * self.SIZE
+        self._check(self.lib.pft_upload_fields(self._h, _ptr(x_padded), mask), "pft_upload_fields")
+
+    def download_fields(self, x_padded: np.ndarray, mask: int):
+        assert x_padded.size == NVAR * self.SIZE
+        self._check(self.lib.pft_download_fields(self._h, _ptr(x_padded), mask), "pft_download_fields")
+
     def upload_interior(self, u=None, p=None, gl=None):
         arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (u, p, gl)]
         for a in arrs:
@@ -132,22 +141,12 @@ class SlabSolver:
         self._check(self.lib.pft_debug_fetch(self._h, which, _ptr(u), _ptr(p)), "pft_debug_fetch")
         return u, p
 
-    def debug_trace(self, max_records: int = 4096):
-        """development builds (libpft_b200_trace.so): (stages, records[n][16]) of the launches since the last call"""
-        rec = np.zeros((max_records, 16), dtype=np.uint64)
-        stg = np.zeros(max_records, dtype=np.int32)
-        n = self.lib.pft_debug_trace(self._h, rec.ctypes.data_as(C.POINTER(C.c_ulonglong)), stg.ctypes.data_as(C.POINTER(C.c_int)), max_records)
-        if n < 0:
-            raise PftError(f"pft_debug_trace failed ({n}): {self.lib.pft_last_error().decode()}")
-        return stg[:n].copy(), rec[:n].copy()
-
-    def debug_trace_cta(self, launches: int = 12):
-        """development builds: per-CTA records [launch][1024][4] (start, end of body, end, smid<<32|chunk)"""
-        out = np.zeros((launches, 1024, 4), dtype=np.uint64)
-        n = self.lib.pft_debug_trace_cta(self._h, out.ctypes.data_as(C.POINTER(C.c_ulonglong)), launches)
-        if n < 0:
-            raise PftError(f"pft_debug_trace_cta failed ({n}): {self.lib.pft_last_error().decode()}")
-        return out[:n]
+    def debug_pow(self, x: np.ndarray, y: float = 0.2) -> np.ndarray:
+        """x**y computed by the DEVICE instance of the step-size controller's pow twin (csrc/pft_pow.h)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        self._check(self.lib.pft_debug_pow(self._h, _ptr(x), float(y), _ptr(out), x.size), "pft_debug_pow")
+        return out
 
     def rasterise(self, spheres_raw: np.ndarray):
         s = np.ascontiguousarray(spheres_raw, dtype=np.float64).reshape(-1, 3)
@@ -205,3 +204,72 @@ class SlabSolver:
 
     def reset_stats(self):
         self._check(self.lib.pft_reset_stats(self._h), "pft_reset_stats")
+
+
+class GroupSolver:
+    """The whole block of a case on several GPUs of ONE host process (pft_group_*): what the reference does
+    with M MPI ranks inside one application run.  Host data is the one padded array of the whole block."""
+
+    def __init__(self, spec: CaseSpec, ngpus: int, devices=None, flags: int = 0, lib_path: str | None = None):
+        self.lib = _lib.load(lib_path)
+        self.spec = spec
+        self.ngpus = ngpus
+        self.n1, self.n2, self.n3 = spec.n1, spec.n2, spec.n3
+        cc = _lib.PftCase(spec.n1, spec.n2, spec.n3, spec.n3, 0, 0, 1, spec.calc_mode, spec.L1, spec.L2, spec.L3)
+        par = spec.param_array()
+        for i in range(_lib.NPARAM):
+            cc.param[i] = float(par[i])
+        dev = (C.c_int * ngpus)(*(devices if devices is not None else range(ngpus)))
+        h = C.c_void_p()
+        rc = self.lib.pft_group_create(C.byref(cc), ngpus, dev, flags, C.byref(h))
+        if rc:
+            raise PftError(f"pft_group_create failed ({rc}): {self.lib.pft_last_error().decode()}")
+        self._h = h
+        self.sys = _lib.PftSystem()
+        self.sys.t, self.sys.h = 0.0, spec.tau
+        self.sys.h_min, self.sys.delta = spec.tau_min, spec.delta
+        self._service_keep = None
+
+    @property
+    def SIZE(self): return (self.n1 + 2 * BT) * (self.n2 + 2 * BT) * (self.n3 + 2 * BT)
+
+    def _check(self, rc, what):
+        if rc:
+            raise PftError(f"{what} failed ({rc}): {self.lib.pft_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.pft_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, x_padded: np.ndarray, mask: int = FIELD_ALL):
+        assert x_padded.size == NVAR * self.SIZE
+        self._check(self.lib.pft_group_upload(self._h, _ptr(x_padded), mask), "pft_group_upload")
+
+    def download(self, x_padded: np.ndarray, mask: int = FIELD_ALL):
+        assert x_padded.size == NVAR * self.SIZE
+        self._check(self.lib.pft_group_download(self._h, _ptr(x_padded), mask), "pft_group_download")
+
+    set_service = SlabSolver.set_service
+
+    def solve(self, final_time: float, max_attempts: int = 0) -> SolveResult:
+        self.sys.max_attempts = max_attempts
+        rc = self.lib.pft_group_solve(self._h, C.byref(self.sys), final_time)
+        if rc not in (0, 1, 2, -4):
+            raise PftError(f"pft_group_solve failed ({rc}): {self.lib.pft_last_error().decode()}")
+        s = self.sys
+        return SolveResult(rc, s.t, s.h, s.steps, s.steps_total, s.rhs_evals, s.last_nan)
+
+    def member_stats(self, r: int) -> dict:
+        st = _lib.PftStats()
+        self._check(self.lib.pft_get_stats(self.lib.pft_group_member(self._h, r), C.byref(st)), "pft_get_stats")
+        d = {n: getattr(st, n) for n, _ in st._fields_ if n not in ("stage_ms", "stage_launches")}
+        d["stage_ms"] = list(st.stage_ms)
+        d["stage_launches"] = list(st.stage_launches)
+        return d

@@ -8,9 +8,14 @@
 // It lets the -m "not gpu" tests check kernel indexing, the fused stage algebra and the
 // integrator's control flow against the oracle on a box without a GPU.
 //
+// Several host threads may launch at the same time (the in-process multi-GPU group drives one
+// "device" per worker thread): the scheduler state is thread-local, `__shared__` variables are
+// per-thread statics, and the system-scope loads/stores of the peer protocol are real atomics, so
+// the halo-flag and error-maximum exchange between slabs is stepped for real on the CPU.
+//
 // It is never loaded by the product: porousfreezethaw_b200/_lib.py only loads libpft_b200.so
-// (nvcc, sm_100a).  It finds no races (fibers run in a fixed order) and says nothing about
-// performance.
+// (nvcc, sm_100a).  It finds no races inside a CTA (fibers run in a fixed order) and says nothing
+// about performance.
 #pragma once
 #ifndef PFT_CUDA_EMU
 #error "cuda_emu/cuda_runtime.h is only for -DPFT_CUDA_EMU builds"
@@ -30,9 +35,9 @@ struct dim3 {
 };
 
 namespace pft_emu {
-extern uint3 g_threadIdx, g_blockIdx;
-extern dim3 g_blockDim, g_gridDim;
-extern unsigned char *g_dyn_smem;
+extern thread_local uint3 g_threadIdx, g_blockIdx;
+extern thread_local dim3 g_blockDim, g_gridDim;
+extern thread_local unsigned char *g_dyn_smem;
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body);
 void syncthreads();
 void yield();                        // let the other fibers of the CTA run (spin-wait loops)
@@ -53,7 +58,7 @@ uint32_t tensor_load_3d(void *dst, const void *map, int x, int y, int z);   // r
 #define __noinline__
 #define __launch_bounds__(...)
 #define __grid_constant__
-#define __shared__ static
+#define __shared__ static thread_local
 #define PFT_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(pft_emu::g_dyn_smem)
 #define PFT_DYN_SMEM_ALIGNED(type, name) type *name = reinterpret_cast<type *>(pft_emu::g_dyn_smem)
 
@@ -87,7 +92,7 @@ struct cudaDeviceProp { int major, minor, multiProcessorCount; char name[64]; };
 
 static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 16; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { memset(p, 0, sizeof *p); p->major = 10; p->minor = 0; p->multiProcessorCount = 4; strcpy(p->name, "emulated sm_100"); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t)malloc(1); return cudaSuccess; }

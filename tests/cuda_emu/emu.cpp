@@ -10,20 +10,20 @@
 
 namespace pft_emu {
 
-uint3 g_threadIdx, g_blockIdx;
-dim3 g_blockDim, g_gridDim;
-unsigned char *g_dyn_smem = nullptr;
+thread_local uint3 g_threadIdx, g_blockIdx;
+thread_local dim3 g_blockDim, g_gridDim;
+thread_local unsigned char *g_dyn_smem = nullptr;
 
 enum { READY = 0, WAITING = 1, DONE = 2 };
 struct Fiber { ucontext_t ctx; int state; uint3 tid; };
 
 static const size_t STACK = 96 * 1024;
-static std::vector<Fiber> fibers;
-static std::vector<unsigned char> stacks;
-static std::vector<unsigned char> smem_buf;
-static ucontext_t sched_ctx;
-static int cur = -1;
-static const std::function<void()> *cur_body = nullptr;
+static thread_local std::vector<Fiber> fibers;
+static thread_local std::vector<unsigned char> stacks;
+static thread_local std::vector<unsigned char> smem_buf;
+static thread_local ucontext_t sched_ctx;
+static thread_local int cur = -1;
+static thread_local const std::function<void()> *cur_body = nullptr;
 
 static void trampoline()
 {
@@ -38,7 +38,7 @@ void syncthreads()
 	swapcontext(&fibers[cur].ctx, &sched_ctx);
 }
 
-static int w_count[64], w_gen[64], w_size[64];
+static thread_local int w_count[64], w_gen[64], w_size[64];
 
 void syncwarp()
 {

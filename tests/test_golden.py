@@ -10,9 +10,9 @@ from oracle import pyoracle as po
 from porousfreezethaw_b200 import cases
 from porousfreezethaw_b200.solver import SlabSolver
 
-# (interval_*.npz are the whole-snapshot-interval records of tests/test_zz_interval_parity.py)
+# (interval_*.npz / partial_*.npz are the step records of tests/test_zz_interval_parity.py, bench_*.npz of bench.py)
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-              if not os.path.basename(p).startswith("interval_"))
+              if not os.path.basename(p).startswith(("interval_", "partial_", "bench_")))
 
 
 def load(path):

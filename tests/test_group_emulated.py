@@ -1,0 +1,87 @@
+"""One host process driving several slabs (pft_group_*, the in-process form of the reference's multi-rank run:
+intertrack.c:1776-1800 slab partition, equation.c:290-326 halo exchange, RK_MPI_SAsolver_hybrid2.c:572 error
+maximum) on the CPU emulation of the CUDA sources: one worker thread per emulated device, so the peer-memory
+protocol of csrc/pft_kernels.cuh -- boundary planes stored into the neighbour's ghost planes, halo flags and
+tickets, the all-to-all of per-slab error maxima inside stage 5, stage 1 skipped after a rejected attempt --
+is stepped for real and checked against the single-rank oracle, bit for bit."""
+import numpy as np
+import pytest
+
+import parity
+from porousfreezethaw_b200 import cases
+from porousfreezethaw_b200.solver import GroupSolver, FLAG_HOST_POW, FLAG_NO_RUNAHEAD
+
+
+def _run(spec, ngpus, emu_lib, T, chunks=2, flags=0, service=False, budget=0):
+    case, orc, w = parity.make(spec)
+    x = w.copy()
+    rec_o, rec_g = [], []
+    s = orc.new_system(t=0.0, h=spec.tau, h_min=spec.tau_min, delta=spec.delta,
+                       service=(lambda ft, t, h, st, tot, ctx: rec_o.append((t, h)) or 0) if service else None)
+    work = np.zeros(5 * x.size)
+    g = GroupSolver(spec, ngpus, lib_path=emu_lib, flags=flags)
+    try:
+        g.upload(w.copy())
+        if service:
+            g.set_service(lambda ft, t, h, st, tot: rec_g.append((t, h)) or 0)
+        for c in range(1, chunks + 1):
+            Tc = T * c / chunks
+            s.max_attempts = budget
+            ro = orc.solve(s, x, Tc, work)
+            r = g.solve(Tc, max_attempts=budget)
+            assert r.code == ro
+            assert (r.t, r.h, r.steps, r.steps_total) == (s.t, s.h, s.steps, s.steps_total), f"chunk {c}"
+        assert rec_g == rec_o
+        got = w.copy()
+        g.download(got)
+        parity.assert_fields(case, got, x, True, f"{ngpus} slabs")
+        # ghost shell of the host array untouched by the download
+        mask = np.ones(got.size, dtype=bool).reshape(3, case.N3, case.N2, case.N1)
+        mask[:, 2:-2, 2:-2, 2:-2] = False
+        assert np.array_equal(got.reshape(mask.shape)[mask], w.reshape(mask.shape)[mask])
+        return r
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("ngpus,mode", [(2, 0), (3, 1), (4, 0), (2, 11), (5, 10)])
+def test_group_adaptive_matches_oracle(emu_lib, ngpus, mode):
+    r = _run(cases.small_case(12, 10, 19, calc_mode=mode), ngpus, emu_lib, T=10.0)
+    if mode in (0, 1):
+        assert r.steps_total > r.steps      # the run contains rejected attempts (stage 1 skipped, flags still advance)
+
+
+def test_group_with_service_callback(emu_lib):
+    _run(cases.small_case(12, 10, 16, calc_mode=0), 3, emu_lib, T=8.0, service=True)
+
+
+@pytest.mark.parametrize("flags", [FLAG_HOST_POW, FLAG_NO_RUNAHEAD])
+def test_group_variants(emu_lib, flags):
+    _run(cases.small_case(12, 10, 16, calc_mode=1), 2, emu_lib, T=8.0, flags=flags)
+
+
+def test_group_budget_resume(emu_lib):
+    _run(cases.small_case(12, 10, 16, calc_mode=0), 2, emu_lib, T=400.0, chunks=3, budget=7)
+
+
+def test_group_break_by_callback(emu_lib):
+    """slab 0's worker asks the callback, every slab stops after the same accepted step"""
+    spec = cases.small_case(12, 10, 16, calc_mode=0)
+    case, orc, w = parity.make(spec)
+    x = w.copy()
+    s = orc.new_system(t=0.0, h=spec.tau, h_min=spec.tau_min, delta=spec.delta, service=lambda ft, t, h, st, tot, ctx: int(st % 5 == 0))
+    work = np.zeros(5 * x.size)
+    g = GroupSolver(spec, 3, lib_path=emu_lib)
+    try:
+        g.upload(w.copy())
+        g.set_service(lambda ft, t, h, st, tot: int(st % 5 == 0))
+        for _ in range(4):
+            ro = orc.solve(s, x, 30.0, work)
+            r = g.solve(30.0)
+            assert r.code == ro
+            assert (r.t, r.h, r.steps, r.steps_total) == (s.t, s.h, s.steps, s.steps_total)
+        got = w.copy()
+        g.download(got)
+        parity.assert_fields(case, got, x, True, "after breaks")
+    finally:
+        g.close()
