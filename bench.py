@@ -175,10 +175,11 @@ def _cpu_reference_run(spec, warmup: int, steps: int, variant: str = "hybrid2", 
     seconds, dict describing the run)."""
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    if threads is not None:       # the OpenMP runtime is already up: change the team size through its API
-        import ctypes
-        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
+    # all host cores, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1): the environment for a runtime
+    # that is not up yet, the API for one that is
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    import ctypes
+    ctypes.CDLL("libgomp.so.1", mode=ctypes.RTLD_GLOBAL).omp_set_num_threads(int(threads if threads is not None else cores))
     os.environ.setdefault("OMP_SCHEDULE", "static")      # apps/intertrack-hybrid-S-freezing/Run:13-19
     os.environ.setdefault("OMP_PROC_BIND", "false")
     po.build("oracle")
@@ -222,8 +223,7 @@ def _cpu_reference_run(spec, warmup: int, steps: int, variant: str = "hybrid2", 
             "sample": f"{n} Merson attempts (5 RHS each) of {spec.name} {spec.n1}x{spec.n2}x{spec.n3} after {warmup} warm-up attempts, "
                       f"{flags}, {dt:.2f} s"}
     if threads is not None:
-        import ctypes
-        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
     return value, n, dt, info
 
 
@@ -248,14 +248,235 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------
 
+def plane_sums(a):
+    """per z-plane sum (mod 2^64) of the float64 bit patterns (tests/golden/make_golden_partial.py)"""
+    return np.ascontiguousarray(a, dtype="<f8").view(np.uint64).reshape(a.shape[0], -1).sum(axis=1, dtype=np.uint64)
+
+
+class Bench:
+    """one workload on this rank's slab: creation, initial state, the timed regions"""
+
+    def __init__(self, args, spec, rank, N, local, lib_path, dry, dist, torch):
+        from porousfreezethaw_b200.solver import SlabSolver
+        self.args, self.spec, self.rank, self.N, self.local, self.dry, self.dist, self.torch = args, spec, rank, N, local, dry, dist, torch
+        self.lib_path = lib_path
+        self.SlabSolver = SlabSolver
+        self.sol = self.new_solver()
+
+    def new_solver(self):
+        sol = self.SlabSolver(self.spec, rank=self.rank, nranks=self.N, device=self.local, lib_path=self.lib_path)
+        if self.N > 1:
+            torch, dist = self.torch, self.dist
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if self.rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(sol.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            sol.comm_init(bytes(uid.cpu().numpy().tobytes()))
+        return sol
+
+    def barrier(self):
+        if self.dry:
+            return
+        self.torch.cuda.synchronize()
+        if self.N > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def allreduce(self, x: float, op: str) -> float:
+        if self.N == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def initial_state(self, sol, device_rasteriser=True):
+        spec = self.spec
+        u, p, gl = spec.initial_fields(first_row=sol.first_row, n3_local=sol.n3)
+        sol.upload_interior(u, p, gl)
+        if device_rasteriser:
+            sol.rasterise(spec.spheres)
+        sol.sys.t, sol.sys.h = float(spec.extra.get("t0", 0.0)), spec.tau      # a restart dataset may set both
+        sol.sys.steps = sol.sys.steps_total = 0
+
+    def advance(self, s, k, H=None):
+        """k step attempts; returns this rank's device time (CUDA events on the solver's stream)"""
+        if H is None:
+            s.solve(self.spec.final_time, max_attempts=k)
+            return s.stats()["device_ms_total"]
+        ms = 0.0
+        for _ in range(k):                                   # one always-accepted Merson step per call (SURVEY.md 8(d))
+            T = s.sys.t + H
+            s.sys.h, s.sys.h_min = T - s.sys.t, float("inf")   # h_eff = fl(fl(t+H) - t): |T - t| <= |h| holds, so the call is ONE attempt
+            s.solve(T)
+            ms += s.stats()["device_ms_total"]
+        return ms
+
+    def timed(self, s, k, repeats, H=None):
+        """`repeats` timed regions of exactly k attempts each, every one bracketed by a barrier and a
+        synchronize on both sides; per region the MAX over ranks of the device time; returns the list"""
+        out = []
+        for _ in range(repeats):
+            self.barrier()
+            t0 = time.perf_counter()
+            my_ms = self.advance(s, k, H)
+            if not self.dry:
+                self.torch.cuda.synchronize()
+            my_wall = 1e3 * (time.perf_counter() - t0)
+            self.barrier()
+            dev = self.allreduce(my_ms, "max")
+            wall = self.allreduce(my_wall, "max")
+            if self.dry and dev <= 0:
+                dev = wall                                   # the emulation has no device clock
+            out.append((dev, wall, my_ms))
+        return out
+
+
+def parity_check(b: Bench, golden_path: str):
+    """The benchmarked workload against the UNMODIFIED reference (tests/golden/partial_<case>.npz: state and
+    per-plane checksums of u and p after the first n attempts): fresh initial state with the sphere pack
+    rasterised by libm tanh on the host (the drop-in plug-in's rasteriser), n attempts on the device(s),
+    every rank checks its own planes."""
+    from porousfreezethaw_b200 import _lib
+    g = np.load(golden_path)
+    n = int(g["break_after"])
+    spec, sol0 = b.spec, b.sol
+    sol = b.new_solver()
+    try:
+        u, p, gl = spec.initial_fields(first_row=sol.first_row, n3_local=sol.n3)
+        w = np.zeros((3, sol.N3, sol.N2, sol.N1))
+        for q, a in enumerate((u, p, gl)):
+            w[q, 2:-2, 2:-2, 2:-2] = a
+        w = w.reshape(-1)
+        _lib.rasterise_host(sol._case, spec.spheres, w)
+        gl_r = w.reshape(3, sol.N3, sol.N2, sol.N1)[2, 2:-2, 2:-2, 2:-2]
+        sol.upload_interior(u, p, np.ascontiguousarray(gl_r))
+        sol.sys.t, sol.sys.h = 0.0, spec.tau
+        r = sol.solve(spec.final_time, max_attempts=n)
+        uo, po_, glo = sol.download_interior()
+        sl = slice(sol.first_row, sol.first_row + sol.n3)
+        mine = (r.t == float(g["state"][0]) and r.h == float(g["state"][1]) and r.steps == int(g["state"][2]) and r.steps_total == int(g["state"][3])
+                and np.array_equal(plane_sums(uo), g["plane_sum_u"][sl]) and np.array_equal(plane_sums(po_), g["plane_sum_p"][sl])
+                and np.array_equal(plane_sums(glo), g["plane_sum_gl"][sl]))
+        ok = b.allreduce(0.0 if mine else 1.0, "sum") == 0.0
+        return {"ok": bool(ok), "against": "unmodified reference, " + os.path.relpath(golden_path, ROOT), "attempts": n,
+                "state": {"t": r.t, "h": r.h, "steps": r.steps, "steps_total": r.steps_total},
+                "reference_state": {"t": float(g["state"][0]), "h": float(g["state"][1]), "steps": int(g["state"][2]), "steps_total": int(g["state"][3])},
+                "fields": "per-plane checksums of u, p, gl: every rank its own planes, bit-exact"}
+    finally:
+        sol.close()
+
+
+def stage_profile(b: Bench, H, peak, peak_src):
+    """per-stage device times: CUDA events around every stage kernel on its stream (programmatic dependent
+    launch off, one attempt in flight).  With several ranks a stage's time includes waiting for the slower
+    neighbour -- use the numbers as kernel times at N = 1 only."""
+    spec = b.spec
+    os.environ["PFT_PROFILE_STAGES"] = "1"
+    solp = b.new_solver()          # (the profiling switch is read when a solver is created)
+    del os.environ["PFT_PROFILE_STAGES"]
+    try:
+        u_, p_, gl_ = b.sol.download_interior()
+        solp.upload_interior(u_, p_, gl_)
+        del u_, p_, gl_
+        solp.sys.t, solp.sys.h, solp.sys.h_min = b.sol.sys.t, b.sol.sys.h, b.sol.sys.h_min
+        b.advance(solp, 3, H)
+        solp.reset_stats()
+        b.barrier()
+        b.advance(solp, b.args.profile_steps, H)
+        b.barrier()
+        stp = solp.stats()
+    finally:
+        solp.close()
+    sb = STAGE_BYTES_HEAT if spec.calc_mode in (0, 1, 2) else STAGE_BYTES_NOHEAT
+    stages = []
+    for i in range(5):
+        nl = stp["stage_launches"][i]
+        if nl == 0:
+            continue
+        ms = stp["stage_ms"][i] / nl
+        if b.dry and ms <= 0:
+            ms = 1e-3
+        gbs = b.sol.cells * sb[i] / (ms * 1e-3) / 1e9
+        stages.append({"stage": i + 1, "launches": nl, "avg_ms": ms, "bytes_per_cell": sb[i], "achieved_gbs": gbs, "frac": gbs / peak})
+    dom = max(stages, key=lambda s: s["avg_ms"] * s["launches"])
+    roofline = {"bound": "hbm", "kernel": f"merson_stage_tma<{dom['stage']}>", "achieved": dom["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b.sol.cells * dom["bytes_per_cell"], "avg_launch_ms": dom["avg_ms"],
+                "per_stage": stages}
+    if b.N > 1:
+        roofline["note"] = "N > 1: a stage's event time includes waiting for the neighbouring slabs' boundary planes"
+    tr = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tr):
+        try:
+            with open(tr) as f:
+                tj = json.load(f)
+            key = f"{spec.name}:stage{dom['stage']}"
+            if key in tj:
+                roofline["traffic"] = tj[key]
+        except Exception:
+            pass
+    return roofline
+
+
+def run_workload(args, name, rank, N, local, lib_path, dry, dist, torch, steps, warmup, repeats, fixed_step, full):
+    """returns (line fragment, Bench).  full: also stage profile, end to end, parity."""
+    spec, scaling, geo = make_spec(name, N)
+    b = Bench(args, spec, rank, N, local, lib_path, dry, dist, torch)
+    sol = b.sol
+    b.initial_state(sol)
+    peak, peak_src = peaks()
+    sb = STAGE_BYTES_HEAT if spec.calc_mode in (0, 1, 2) else STAGE_BYTES_NOHEAT
+
+    # ---- warm-up, then `repeats` regions of EXACTLY `steps` attempts, device-resident ---------------
+    sol.solve(spec.final_time, max_attempts=warmup)
+    H = 0.5 * sol.sys.h if fixed_step else None              # fixed-step mode: identical on every rank
+    if fixed_step:
+        b.advance(sol, 3, H)
+    st0 = sol.stats()
+    ev0 = sol.sys.rhs_evals
+    regions = b.timed(sol, steps, repeats, H)
+    st1 = sol.stats()
+    devs = sorted(r[0] for r in regions)
+    dev_ms = statistics.median(devs)
+    wall_ms = statistics.median(sorted(r[1] for r in regions))
+    attempts_all = st1["attempts"] - st0["attempts"]
+    rhs_all = sol.sys.rhs_evals - ev0
+    rhs_per_region = rhs_all / max(repeats, 1)
+    total_cells = b.allreduce(float(sol.cells), "sum")
+    value = total_cells * rhs_per_region / (dev_ms * 1e-3) / 1e6
+    stage_launches = [(a - c) / max(repeats, 1) for a, c in zip(st1["stage_launches"], st0["stage_launches"])]
+    # real work only: launches that found the integration finished are not counted as bytes moved
+    noop = (st1["noop_launches"] - st0["noop_launches"]) / max(repeats, 1)
+    skipped1 = attempts_all / max(repeats, 1) - (rhs_per_region - 4 * attempts_all / max(repeats, 1))      # stage 1 launches that returned at once (K1 reused)
+    eff = [stage_launches[0] - noop / 5 - skipped1] + [n_ - noop / 5 for n_ in stage_launches[1:]]
+    step_gbs = total_cells / N * sum(bb * n_ for bb, n_ in zip(sb, eff)) / (dev_ms * 1e-3) / 1e9
+    frag = {
+        "workload": spec.name, "grid": [spec.n1, spec.n2, spec.n3], "calc_mode": spec.calc_mode, "scaling": scaling,
+        "mode": f"fixed step H={H:.6g}" if fixed_step else "adaptive (delta 1e-3)",
+        "value": value, "unit": "Mcell-RHS/s", "steps": steps, "repeats": repeats, "ms_per_step": dev_ms / steps,
+        "device_ms_regions": [round(d, 4) for d in devs], "wall_ms_per_step": wall_ms / steps,
+        "rhs_evals_per_attempt": rhs_per_region / steps,
+        "roofline_step": {"achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+                          "note": "algorithmic bytes of the stage kernels that did work in a timed region / its device time, per GPU (launch gaps included)"},
+    }
+    info = {"spec": spec, "scaling": scaling, "geo": geo, "H": H, "st0": st0, "st1": st1, "regions": regions, "peak": peak, "peak_src": peak_src,
+            "launches": (st1["kernel_launches"] - st0["kernel_launches"]) / max(repeats, 1), "total_cells": total_cells}
+    return frag, b, info
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--repeats", type=int, default=7, help="timed regions of --steps attempts each; the median is reported")
     ap.add_argument("--workload", default=os.environ.get("PFT_BENCH_WORKLOAD", "400-SigmaP1-P-smallsigma"))
+    ap.add_argument("--also", default=os.environ.get("PFT_BENCH_ALSO", "default"),
+                    help="comma-separated secondary workloads reported under `also` ('none' to skip); default: the PhysRevE-2025 200 case and "
+                         "the SURVEY 8(d)-5 weak-scaling slab 800x800x(100 N) in fixed-step mode")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--variant", default="strict", choices=["strict", "fast"],
                     help="strict = IEEE association, bit-exact (default); fast = FMA contraction allowed (fields within 1e-10, no step-sequence parity)")
     ap.add_argument("--fixed-step", action="store_true",
@@ -267,13 +488,14 @@ def main():
         args.warmup = 3          # the timing rules ask for W >= 3 (and 0 would mean "no attempt limit" to pft_solve)
     if args.steps < 1:
         args.steps = 1
+    if args.repeats < 1:
+        args.repeats = 1
 
     if args.impl == "reference":
         return run_reference_arm(args)
 
     import torch
     import torch.distributed as dist
-    from porousfreezethaw_b200.solver import SlabSolver
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -298,167 +520,86 @@ def main():
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
     N = world
 
-    spec, scaling, geo = make_spec(args.workload, N)
     from porousfreezethaw_b200 import _lib as _pftlib
     lib_path = _pftlib.FAST_LIB_PATH if args.variant == "fast" else None
     if os.environ.get("PFT_BENCH_LIB"):       # A/B builds (development)
         lib_path = os.environ["PFT_BENCH_LIB"]
     if dry:
         lib_path = dry
-    sol = SlabSolver(spec, rank=rank, nranks=N, device=local, lib_path=lib_path)
-    if N > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(sol.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        sol.comm_init(bytes(uid.cpu().numpy().tobytes()))
 
-    # initial condition of this rank's slab, sphere pack rasterised on the device
-    u, p, gl = spec.initial_fields(first_row=sol.first_row, n3_local=sol.n3)
-    sol.upload_interior(u, p, gl)
-    sol.rasterise(spec.spheres)
-    del u, p, gl
-    sol.sys.t, sol.sys.h = float(spec.extra.get("t0", 0.0)), spec.tau      # a restart dataset may set both
+    # clocks / throttle reasons are sampled over the whole measurement (started BEFORE any barrier that
+    # precedes a timed region, stopped after the last one), on rank 0's GPU
+    sampler = ClockSampler(local) if (rank == 0 and not dry) else None
 
-    def barrier():
-        if dry:
-            return
-        torch.cuda.synchronize()
-        if N > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def allmax(x: float) -> float:
-        if N == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x: float) -> float:
-        if N == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    T_END = spec.final_time
-
-    # ---- warm-up, then EXACTLY K attempts, device-resident --------------------------------
-    sol.solve(T_END, max_attempts=args.warmup)
-    H = 0.5 * sol.sys.h                                      # fixed-step mode: identical on every rank
-
-    def advance(s, k):
-        """k step attempts; returns this rank's device time (CUDA events on the solver's stream)"""
-        if not args.fixed_step:
-            s.solve(T_END, max_attempts=k)
-            return s.stats()["device_ms_total"]
-        ms = 0.0
-        for _ in range(k):                                   # one always-accepted Merson step per call (SURVEY.md 8(d))
-            s.sys.h, s.sys.h_min = H, float("inf")
-            s.solve(s.sys.t + H)
-            ms += s.stats()["device_ms_total"]
-        return ms
-
-    if args.fixed_step:
-        advance(sol, 3)
-    st0 = sol.stats()
-    ev0 = sol.sys.rhs_evals
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    t_wall = time.perf_counter()
-    my_ms = advance(sol, args.steps)
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    clocks = sampler.stop() if sampler else None
-    st1 = sol.stats()
-    dev_ms = allmax(my_ms)                                   # max over ranks
-    if dry and dev_ms <= 0:
-        dev_ms = 1e3 * t_wall                                # the emulation has no device clock
-    attempts = st1["attempts"] - st0["attempts"]
-    rhs = sol.sys.rhs_evals - ev0
-    total_cells = allsum(float(sol.cells))
-    value = total_cells * rhs / (dev_ms * 1e-3) / 1e6
-    launches = st1["kernel_launches"] - st0["kernel_launches"]
-    stage_launches = [a - b for a, b in zip(st1["stage_launches"], st0["stage_launches"])]
-    # host side of the control loop, per attempt: time blocked on the device's decision / time issuing launches
-    host_wait = (st1["host_wait_ms"] - st0["host_wait_ms"]) / max(attempts, 1)
-    host_launch = (st1["host_launch_ms"] - st0["host_launch_ms"]) / max(attempts, 1)
+    frag, b, info = run_workload(args, args.workload, rank, N, local, lib_path, dry, dist, torch,
+                                 args.steps, args.warmup, args.repeats, args.fixed_step, True)
+    spec, sol, H = info["spec"], b.sol, info["H"]
+    st0, st1 = info["st0"], info["st1"]
+    attempts = args.steps
+    # host side of the control loop, per attempt: time asleep waiting for a free slot of the launch queue / time issuing launches
+    tot_att = max(st1["attempts"] - st0["attempts"], 1)
+    host_wait = (st1["host_wait_ms"] - st0["host_wait_ms"]) / tot_att
+    host_launch = (st1["host_launch_ms"] - st0["host_launch_ms"]) / tot_att
+    my_dev = statistics.median(sorted(r[2] for r in info["regions"])) / attempts
     if N > 1:
         hw = [None] * N
-        dist.all_gather_object(hw, (round(host_wait, 4), round(host_launch, 4), round(my_ms / max(attempts, 1), 4)))
+        dist.all_gather_object(hw, (round(host_wait, 4), round(host_launch, 4), round(my_dev, 4)))
     else:
-        hw = [(round(host_wait, 4), round(host_launch, 4), round(my_ms / max(attempts, 1), 4))]
+        hw = [(round(host_wait, 4), round(host_launch, 4), round(my_dev, 4))]
 
-    # ---- per-stage device times (CUDA events around every stage kernel on its stream) ----
-    os.environ["PFT_PROFILE_STAGES"] = "1"
-    # (a second solver object: the profiling switch is read when a solver is created)
-    u_, p_, gl_ = sol.download_interior()
-    solp = SlabSolver(spec, rank=rank, nranks=N, device=local, lib_path=lib_path)
-    if N > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(solp.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        solp.comm_init(bytes(uid.cpu().numpy().tobytes()))
-    solp.upload_interior(u_, p_, gl_)
-    solp.sys.t, solp.sys.h = sol.sys.t, sol.sys.h
-    del u_, p_, gl_
-    solp.sys.h_min = sol.sys.h_min
-    advance(solp, 3)
-    solp.reset_stats()
-    barrier()
-    advance(solp, args.profile_steps)
-    barrier()
-    stp = solp.stats()
-    del os.environ["PFT_PROFILE_STAGES"]
-    sb = STAGE_BYTES_HEAT if spec.calc_mode in (0, 1, 2) else STAGE_BYTES_NOHEAT
-    peak, peak_src = peaks()
-    stages = []
-    for i in range(5):
-        nl = stp["stage_launches"][i]
-        if nl == 0:
-            continue
-        ms = stp["stage_ms"][i] / nl
-        if dry and ms <= 0:
-            ms = 1e-3
-        gbs = sol.cells * sb[i] / (ms * 1e-3) / 1e9
-        stages.append({"stage": i + 1, "launches": nl, "avg_ms": ms, "bytes_per_cell": sb[i], "achieved_gbs": gbs, "frac": gbs / peak})
-    dom = max(stages, key=lambda s: s["avg_ms"] * s["launches"])
-    roofline = {"bound": "hbm", "kernel": f"merson_stage<{dom['stage']}>", "achieved": dom["achieved_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": sol.cells * dom["bytes_per_cell"], "avg_launch_ms": dom["avg_ms"],
-                "per_stage": stages}
-    tr = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes per launch from the committed ncu capture
-    if os.path.exists(tr):
-        try:
-            with open(tr) as f:
-                tj = json.load(f)
-            key = f"{spec.name}:stage{dom['stage']}"
-            if key in tj:
-                roofline["traffic"] = tj[key]
-        except Exception:
-            pass
-    solp.close()
+    clocks = sampler.stop() if sampler else None            # the headline regions are over
+
+    roofline = stage_profile(b, H, info["peak"], info["peak_src"])
 
     # ---- end to end: pinned HOST buffers -> upload -> K attempts -> download ---------------
+    # what RK_MPI_SA_solve does per call with a host-resident x: the temperature and phase fields travel both
+    # ways, the static glass field is resident (csrc/rk_mpi_sa_b200.c)
+    from porousfreezethaw_b200.solver import FIELD_U, FIELD_P
     xh = np.empty(3 * sol.SIZE) if dry else torch.empty(3 * sol.SIZE, dtype=torch.float64, pin_memory=True).numpy()
     sol.download(xh)                                         # a valid padded host image of the current state
-    barrier()
-    ev0 = sol.sys.rhs_evals
-    a0 = sol.sys.steps_total
-    t0 = time.perf_counter()
-    sol.upload(xh)
-    advance(sol, args.steps)
-    sol.download(xh)
-    barrier()
-    e2e_s = allmax(time.perf_counter() - t0)
-    e2e_attempts = sol.sys.steps_total - a0
-    e2e_value = total_cells * (sol.sys.rhs_evals - ev0) / e2e_s / 1e6
-    nbytes = 3 * sol.SIZE * 8
-    e2e = {"value": e2e_value, "unit": "Mcell-RHS/s", "h2d_bytes_per_step": nbytes / max(e2e_attempts, 1),
-           "d2h_bytes_per_step": nbytes / max(e2e_attempts, 1), "attempts": e2e_attempts,
-           "note": "one solve call = upload(x) + K attempts + download(x), as RK_MPI_SA_solve with a host-resident x"}
+    e2e_runs = []
+    for k_e2e in (attempts, 10 * attempts):
+        b.barrier()
+        ev0 = sol.sys.rhs_evals
+        a0 = sol.sys.steps_total
+        t0 = time.perf_counter()
+        sol.upload_fields(xh, FIELD_U | FIELD_P)
+        b.advance(sol, k_e2e, H)
+        sol.download_fields(xh, FIELD_U | FIELD_P)
+        b.barrier()
+        e2e_s = b.allreduce(time.perf_counter() - t0, "max")
+        e2e_runs.append((sol.sys.steps_total - a0, info["total_cells"] * (sol.sys.rhs_evals - ev0) / e2e_s / 1e6, e2e_s))
+    nbytes = 2 * sol.n3 * sol.N1 * sol.N2 * 8               # u and p, the slab's planes incl. their x/y ghost nodes
+    e2e = {"value": e2e_runs[0][1], "unit": "Mcell-RHS/s", "h2d_bytes_per_step": nbytes / max(e2e_runs[0][0], 1),
+           "d2h_bytes_per_step": nbytes / max(e2e_runs[0][0], 1), "attempts": e2e_runs[0][0],
+           "long_call": {"attempts": e2e_runs[1][0], "value": e2e_runs[1][1], "seconds": e2e_runs[1][2]},
+           "note": "one solve call = upload(u, p) + K attempts + download(u, p) through the C ABI with pinned host buffers, as RK_MPI_SA_solve "
+                   "with a host-resident x (gl is static and stays on the device); long_call = the same with 10 K attempts"}
+
+    # ---- parity of THIS workload against the unmodified reference -------------------------
+    parity = None
+    gpath = os.path.join(ROOT, "tests", "golden", f"partial_{spec.name}.npz")
+    if not args.no_parity and not args.fixed_step and args.variant == "strict" and os.path.exists(gpath) and "plane_sum_u" in np.load(gpath) \
+            and os.path.exists(_pftlib.RK_LIB_PATH) and not dry:
+        try:
+            parity = parity_check(b, gpath)
+        except Exception as e:
+            parity = {"ok": False, "error": repr(e)}
+
+    # ---- secondary workloads -------------------------------------------------------------
+    also = []
+    names = [] if args.also in ("none", "") else (["2025-200-GradP", "cube-800w"] if args.also == "default" else args.also.split(","))
+    if dry:
+        names = []
+    for nm in names:
+        try:
+            fixed = nm.endswith("w")
+            f2, b2, i2 = run_workload(args, nm, rank, N, local, lib_path, dry, dist, torch,
+                                      30 if fixed else args.steps, 10 if fixed else args.warmup, 3, fixed, False)
+            b2.sol.close()
+            also.append(f2)
+        except Exception as e:
+            also.append({"workload": nm, "error": repr(e)})
 
     # ---- the reference CPU path on this host (rank 0, N == 1 only) ------------------------
     cpu = None
@@ -479,23 +620,24 @@ def main():
     if rank == 0:
         st = sol.stats()
         line = {
-            "metric": "Mcell-RHS evals/s", "value": value, "unit": "Mcell-RHS/s", "n_gpus": N,
-            "steps": attempts, "warmup": args.warmup, "ms_per_step": dev_ms / max(attempts, 1),
-            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+            "metric": "Mcell-RHS evals/s", "value": frag["value"], "unit": "Mcell-RHS/s", "n_gpus": N,
+            "steps": attempts, "warmup": args.warmup, "ms_per_step": frag["ms_per_step"],
+            "higher_is_better": True, "scaling": info["scaling"], "vs_baseline": None, "dtype": "f64",
             "data": "DRY RUN on the CPU emulation (tests only): not a measurement" if dry else "synthetic",
             "config": {"workload": spec.name, "grid": [spec.n1, spec.n2, spec.n3], "calc_mode": spec.calc_mode,
-                       "geometry": geo, "mode": f"fixed step H={H:.6g}" if args.fixed_step else "adaptive (delta 1e-3)", "variant": args.variant, "cache": "inputs larger than L2 (no flush needed)"
-                       if sol.cells * 13 * 8 > 2 * 126e6 else "working set fits L2",
+                       "geometry": info["geo"], "mode": frag["mode"], "variant": args.variant,
+                       "cache": "inputs larger than L2 (no flush needed)" if sol.cells * 13 * 8 > 2 * 126e6 else "working set fits L2",
                        "parallelism": f"z-slabs x{N}", "tile": [st["tile_x"], st["tile_y"]], "z_chunk": st["z_chunk"],
-                       "rhs_evals_per_attempt": rhs / max(attempts, 1),
-                       "accepted": st1["accepted"] - st0["accepted"]},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "wall_ms_per_step": 1e3 * t_wall / max(attempts, 1),
-            "host_loop_ms_per_step": {"per_rank[wait, launch, device]": hw},
-            "roofline_step": {"achieved": total_cells / N * sum(b * n for b, n in zip(sb, stage_launches)) / (dev_ms * 1e-3) / 1e9,
-                              "peak": peak, "unit": "GB/s",
-                              "frac": total_cells / N * sum(b * n for b, n in zip(sb, stage_launches)) / (dev_ms * 1e-3) / 1e9 / peak,
-                              "note": "algorithmic bytes of every stage kernel launched in the timed region / device time, per GPU (includes launch gaps and host round trips)"},
+                       "rhs_evals_per_attempt": frag["rhs_evals_per_attempt"],
+                       "timing": f"median of {args.repeats} regions of {attempts} attempts, each: barrier + synchronize, CUDA events on the solver stream, max over ranks",
+                       "controller": "device (twin of the host libm pow), attempts enqueued ahead: %d" % st["runahead"] if st["device_pow"] else "host pow per attempt"},
+            "e2e": e2e, "gpu_launches": info["launches"], "clocks": clocks, "roofline": roofline,
+            "device_ms_regions": frag["device_ms_regions"],
+            "wall_ms_per_step": frag["wall_ms_per_step"],
+            "host_loop_ms_per_step": {"per_rank[asleep, launching, device]": hw},
+            "roofline_step": frag["roofline_step"],
+            "parity": parity,
+            "also": also,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

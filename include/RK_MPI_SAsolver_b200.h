@@ -20,7 +20,7 @@
 #ifdef PFT_HAVE_MPI
 #include <mpi.h>
 #else
-#include "mpi.h"      /* oracle/shim/mpi.h: single-rank token types when no MPI is installed */
+#include "mpi_single/mpi.h"   /* single-rank token types when no MPI is installed */
 #endif
 
 #ifndef PFT_FLOAT_DEFINED

@@ -20,12 +20,19 @@ extern "C" {
 #endif
 
 /* Create (or re-create) the device solver for this rank's block.  Called from PrecalculateData
- * once the block geometry and model parameters are known.  Returns 0 or a PFT_E* code. */
+ * once the block geometry and model parameters are known.  Returns 0 or a PFT_E* code.
+ * Environment: PFT_NGPUS=n (> 1, single-rank runs only): this ONE host process cuts its block into n
+ * z-slabs (intertrack.c:1780-1787) on the devices PFT_DEVICES="0,1,.." (default 0..n-1);
+ * otherwise one GPU per process: PFT_DEVICE / LOCAL_RANK / OMPI_COMM_WORLD_LOCAL_RANK. */
 int pft_equation_configure(const pft_case *c);
 
-/* The solver object configured above (NULL if none): what RK_MPI_SA_solve drives. */
+/* What RK_MPI_SA_solve drives: the solver object configured above, or the multi-GPU group (exactly one
+ * of the two is non-NULL after a successful configuration). */
 pft_solver *pft_equation_solver(void);
+pft_group *pft_equation_group(void);
 const pft_case *pft_equation_case(void);
+/* counts configurations: the static glass field is uploaded once per configuration */
+int pft_equation_generation(void);
 
 /* Destroy the device solver (FreePrecalcData). */
 void pft_equation_release(void);

@@ -24,42 +24,80 @@ enum {
 	Q_u_noise_amp, Q_ball_radius
 };
 
-static pft_solver *g_solver = NULL;
+static pft_solver *g_solver = NULL;      /* one GPU per host process ... */
+static pft_group *g_group = NULL;        /* ... or one host process driving PFT_NGPUS GPUs */
 static pft_case g_case;
+static int g_generation = 0;             /* bumped by every (re)configuration: the glass field has to be uploaded again */
+
+/* PFT_DEVICES="0,2,4,6" or 0..n-1 */
+static void device_list(int n, int *dev)
+{
+	const char *e = getenv("PFT_DEVICES");
+	int i;
+	for (i = 0; i < n; i++) dev[i] = i;
+	for (i = 0; e && *e && i < n; i++) {
+		dev[i] = atoi(e);
+		e = strchr(e, ',');
+		if (e) e++;
+	}
+}
 
 int pft_equation_configure(const pft_case *c)
 {
-	int dev = 0, rc;
+	int dev = 0, rc, ngpus = 1;
 	const char *e;
 	if (!c) return PFT_EINVAL;
 	pft_equation_release();
-	/* one process per GPU: LOCAL_RANK (torchrun) / OMPI_COMM_WORLD_LOCAL_RANK / PFT_DEVICE pick the device */
-	if ((e = getenv("PFT_DEVICE")) && *e) dev = atoi(e);
-	else if ((e = getenv("LOCAL_RANK")) && *e) dev = atoi(e);
-	else if ((e = getenv("OMPI_COMM_WORLD_LOCAL_RANK")) && *e) dev = atoi(e);
-	else if ((e = getenv("MV2_COMM_WORLD_LOCAL_RANK")) && *e) dev = atoi(e);
-	rc = pft_create(c, dev, 0u, &g_solver);
-	if (rc) {
-		fprintf(stderr, "pft_equation_configure: %s\n", pft_last_error());
-		g_solver = NULL;
-		return rc;
+	if ((e = getenv("PFT_NGPUS")) && *e) ngpus = atoi(e);
+	if (ngpus > 1 && c->nranks == 1) {
+		/* ONE host process (a single MPI rank, or no MPI at all) owns the whole block and cuts it into
+		   PFT_NGPUS z-slabs itself, by the reference's own rule (intertrack.c:1780-1787) */
+		int devs[64];
+		if (ngpus > 64) ngpus = 64;
+		device_list(ngpus, devs);
+		rc = pft_group_create(c, ngpus, devs, 0u, &g_group);
+		if (rc) {
+			fprintf(stderr, "pft_equation_configure: %s\n", pft_last_error());
+			g_group = NULL;
+			return rc;
+		}
+	} else {
+		/* one process per GPU: LOCAL_RANK (torchrun) / OMPI_COMM_WORLD_LOCAL_RANK / PFT_DEVICE pick the device */
+		if ((e = getenv("PFT_DEVICE")) && *e) dev = atoi(e);
+		else if ((e = getenv("LOCAL_RANK")) && *e) dev = atoi(e);
+		else if ((e = getenv("OMPI_COMM_WORLD_LOCAL_RANK")) && *e) dev = atoi(e);
+		else if ((e = getenv("MV2_COMM_WORLD_LOCAL_RANK")) && *e) dev = atoi(e);
+		rc = pft_create(c, dev, 0u, &g_solver);
+		if (rc) {
+			fprintf(stderr, "pft_equation_configure: %s\n", pft_last_error());
+			g_solver = NULL;
+			return rc;
+		}
 	}
 	g_case = *c;
+	g_generation++;
 	return 0;
 }
 
 pft_solver *pft_equation_solver(void) { return g_solver; }
-const pft_case *pft_equation_case(void) { return g_solver ? &g_case : NULL; }
+pft_group *pft_equation_group(void) { return g_group; }
+const pft_case *pft_equation_case(void) { return (g_solver || g_group) ? &g_case : NULL; }
+int pft_equation_generation(void) { return g_generation; }
 
 void pft_equation_release(void)
 {
 	if (g_solver) { pft_destroy(g_solver); g_solver = NULL; }
+	if (g_group) { pft_group_destroy(g_group); g_group = NULL; }
 }
 
 /* ---- the right-hand sides handed out by the meta-pointers ---------------------------------- */
 
 static void device_rhs(double t, const double *w, double *dw)
 {
+	if (g_group) {
+		fprintf(stderr, "porousfreezethaw_b200: a single right-hand-side evaluation with host buffers is not offered for a multi-GPU group (PFT_NGPUS > 1)\n");
+		abort();
+	}
 	if (!g_solver) {
 		fprintf(stderr, "porousfreezethaw_b200: right-hand side called before PrecalculateData configured the device solver\n");
 		abort();     /* there is no CPU path to fall back to */

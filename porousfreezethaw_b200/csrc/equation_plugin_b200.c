@@ -89,6 +89,19 @@ int PrecalculateData(FLOAT *var_eps_mult)
 
 	error_code = pft_equation_configure(&c) ? 1 : 0;
 	CheckErrorAcrossRanks(error_code, 1, Device_errors);
+
+	/* several ranks, one GPU each: the slabs find each other (NCCL bootstrap, then peer memory over NVLink;
+	   include/pft_b200.h).  The 128-byte id travels the way the reference moves its setup data: MPI_Bcast. */
+	if (MPIprocs > 1) {
+		unsigned char comm_id[128];
+		error_code = 0;
+		if (MPIrank == 0) error_code = pft_comm_unique_id(comm_id) ? 1 : 0;
+		CheckErrorAcrossRanks(error_code, 1, Device_errors);
+		MPI_Bcast(comm_id, 128, MPI_BYTE, MPIrankmap[0], MPI_COMM_WORLD);
+		error_code = pft_comm_init(pft_equation_solver(), comm_id) ? 1 : 0;
+		if (error_code) Mmprintf(logfile, "ERROR: %s\n", pft_last_error());
+		CheckErrorAcrossRanks(error_code, 1, Device_errors);
+	}
 	return 0;
 }
 

@@ -7,7 +7,11 @@
  * Makefile (apps/intertrack-hybrid-S-freezing/Makefile:15).
  *
  * Host code in C; everything numerical happens behind the C ABI of libpft_b200.so:
- *   RK_MPI_SA_solve = pft_upload(system->x) + pft_solve(...) + pft_download(system->x).
+ *   RK_MPI_SA_solve = pft_upload_fields(system->x) + pft_solve(...) + pft_download_fields(system->x)
+ * (or the pft_group_* forms when this one process drives several GPUs, PFT_NGPUS).  Of system->x only
+ * the temperature and phase fields travel per call; the glass field is static (dgl/dt == 0,
+ * equation.c:731) and is uploaded once per configuration.  The caller's array is page-locked on first
+ * use so that the copies run at PCIe speed.
  * The right-hand side returned by system->meta_f() must be one of the device right-hand sides of
  * the B200 model plug-in (pft_f_device_model01/2); a foreign host function is refused with -2 --
  * there is no CPU path.
@@ -28,6 +32,14 @@ static int handle_NAN = 0;          /* :63 */
 static int last_NAN = 0;            /* :64 */
 static MPI_Comm RKcomm;
 static int RKrank = 0, RKprocs = 1, RKmaster = 0;
+static int gl_generation = -1;      /* configuration whose glass field is resident on the device(s) */
+static void *pinned_x = NULL;       /* the caller's solution array, page-locked by this module */
+
+static int env_on(const char *name)
+{
+	const char *e = getenv(name);
+	return e && *e && *e != '0';
+}
 
 /* RK_MPI_SAsolver_hybrid2.c:72-120.  No host scratch is allocated: K1,K3,K4 and the stage
  * buffers live in HBM and belong to the pft_solver object. */
@@ -48,6 +60,8 @@ int RK_MPI_SA_cleanup(void)
 {
 	if (max_n == 0) return -3;
 	max_n = 0;
+	if (pinned_x) { pft_host_unregister(pinned_x); pinned_x = NULL; }
+	gl_generation = -1;
 	return 0;
 }
 
@@ -93,15 +107,20 @@ static int chunks_match_block(const RK_MEM_DIST *n, const pft_case *c)
 
 typedef struct { RK_MPI_S_SOLUTION *system; } service_ctx;
 
-/* RK_MPI_SAsolver_hybrid2.c:676-685: the callback sees the current t and h in the structure */
+/* RK_MPI_SAsolver_hybrid2.c:676-685: the callback sees the current t and h in the structure.  It is installed
+ * in the master rank only (intertrack.c:2173); the reference re-broadcasts the command word after it (:690)
+ * so that a break stops every rank after the same step -- here the master's verdict is broadcast. */
 static int service_trampoline(double final_time, double t, double h, long steps, long steps_total, void *ctx)
 {
 	RK_MPI_S_SOLUTION *system = ((service_ctx *)ctx)->system;
+	int stop = 0;
 	system->t = t;
 	system->h = h;
 	system->steps = steps;
 	system->steps_total = steps_total;
-	return system->Service_Callback(final_time, system);
+	if (system->Service_Callback) stop = system->Service_Callback(final_time, system) ? 1 : 0;
+	if (RKprocs > 1) MPI_Bcast(&stop, 1, MPI_INT, RKmaster, RKcomm);
+	return stop;
 }
 
 /* RK_MPI_SAsolver_hybrid2.c:215-770 */
@@ -110,9 +129,12 @@ int RK_MPI_SA_solve(FLOAT final_time, RK_MPI_S_SOLUTION *system)
 	int error_code = 0, errcode_from_others = 0, rc;
 	RK_RightHandSide f = NULL;
 	pft_solver *solver;
+	pft_group *group;
 	const pft_case *blk;
 	pft_system ps;
 	service_ctx sctx;
+	unsigned up_mask;
+	int have_callback;
 
 	if (system == NULL) return -2;                                  /* :249 */
 	if (system->meta_f != NULL) f = system->meta_f();               /* :268 */
@@ -125,13 +147,14 @@ int RK_MPI_SA_solve(FLOAT final_time, RK_MPI_S_SOLUTION *system)
 	if (RKrank == RKmaster && system->delta <= 0) error_code = -2;
 
 	solver = pft_equation_solver();
+	group = pft_equation_group();
 	blk = pft_equation_case();
 	if (!error_code) {
 		if (f == NULL || !pft_equation_is_device_rhs(f)) {
 			fprintf(stderr, "RK_MPI_SA_solve (B200): meta_f() returned a host right-hand side; only the device right-hand "
 			                "sides of the B200 model plug-in are supported (no CPU path)\n");
 			error_code = -2;
-		} else if (solver == NULL || blk == NULL) {
+		} else if ((solver == NULL && group == NULL) || blk == NULL) {
 			fprintf(stderr, "RK_MPI_SA_solve (B200): the model plug-in has not configured a device solver (PrecalculateData)\n");
 			error_code = -3;
 		} else if (system->DDLBF_Rearrange != NULL) {
@@ -170,13 +193,29 @@ int RK_MPI_SA_solve(FLOAT final_time, RK_MPI_S_SOLUTION *system)
 	ps.max_attempts = 0;
 	ps.rhs_evals = 0;
 	sctx.system = system;
-	ps.service = system->Service_Callback ? service_trampoline : NULL;
+	/* every rank has to stop after the same accepted step: if the master has a callback, all ranks take part */
+	have_callback = (RKrank == RKmaster && system->Service_Callback) ? 1 : 0;
+	MPI_Bcast(&have_callback, 1, MPI_INT, RKmaster, RKcomm);
+	ps.service = have_callback ? service_trampoline : NULL;
 	ps.service_ctx = &sctx;
 
-	rc = pft_upload(solver, system->x);
-	if (rc) { fprintf(stderr, "RK_MPI_SA_solve (B200): %s\n", pft_last_error()); return -6; }
+	/* page-lock the caller's array once (pageable memory halves the PCIe rate); failure is harmless */
+	if (pinned_x != (void *)system->x && !env_on("PFT_NO_PIN")) {
+		const int last = system->n->n_chunks - 1;
+		const unsigned long long bytes = sizeof(FLOAT) * (unsigned long long)max_n;
+		(void)last;
+		if (pinned_x) { pft_host_unregister(pinned_x); pinned_x = NULL; }
+		if (pft_host_register(system->x, bytes) == 0) pinned_x = (void *)system->x;
+	}
 
-	rc = pft_solve(solver, &ps, final_time);
+	/* the glass field is static: it goes up once per configuration of the plug-in */
+	up_mask = PFT_FIELD_U | PFT_FIELD_P;
+	if (gl_generation != pft_equation_generation() || env_on("PFT_UPLOAD_GL_ALWAYS")) up_mask |= PFT_FIELD_GL;
+	rc = group ? pft_group_upload(group, system->x, up_mask) : pft_upload_fields(solver, system->x, up_mask);
+	if (rc) { fprintf(stderr, "RK_MPI_SA_solve (B200): %s\n", pft_last_error()); return -6; }
+	gl_generation = pft_equation_generation();
+
+	rc = group ? pft_group_solve(group, &ps, final_time) : pft_solve(solver, &ps, final_time);
 	if (rc < 0 && rc != PFT_SOLVE_NAN && rc != PFT_SOLVE_BADSYSTEM) {
 		fprintf(stderr, "RK_MPI_SA_solve (B200): %s\n", pft_last_error());
 		return -6;
@@ -190,6 +229,9 @@ int RK_MPI_SA_solve(FLOAT final_time, RK_MPI_S_SOLUTION *system)
 	   and before every callback (:679); otherwise left alone */
 	system->h = ps.h;
 
-	if (pft_download(solver, system->x)) { fprintf(stderr, "RK_MPI_SA_solve (B200): %s\n", pft_last_error()); return -6; }
+	if (group ? pft_group_download(group, system->x, PFT_FIELD_U | PFT_FIELD_P) : pft_download_fields(solver, system->x, PFT_FIELD_U | PFT_FIELD_P)) {
+		fprintf(stderr, "RK_MPI_SA_solve (B200): %s\n", pft_last_error());
+		return -6;
+	}
 	return rc;
 }

@@ -33,6 +33,12 @@ def digest(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a, dtype="<f8").tobytes()).hexdigest()
 
 
+def plane_sums(a: np.ndarray) -> np.ndarray:
+    """per z-plane sum (mod 2^64) of the float64 bit patterns: a checksum every slab owner can compute for
+    its own planes (bench.py's multi-GPU `parity` key)"""
+    return np.ascontiguousarray(a, dtype="<f8").view(np.uint64).reshape(a.shape[0], -1).sum(axis=1, dtype=np.uint64)
+
+
 def main():
     for arg in sys.argv[1:]:
         name, n = arg.rsplit(":", 1)
@@ -56,6 +62,7 @@ def main():
                             state=np.array([t, h, steps, total]), record=rec,
                             sha_u=digest(x[0]), sha_p=digest(x[1]), sha_gl=digest(x[2]),
                             sample_u=x[0][::sz, ::sy, ::sx].copy(), sample_p=x[1][::sz, ::sy, ::sx].copy(),
+                            plane_sum_u=plane_sums(x[0]), plane_sum_p=plane_sums(x[1]), plane_sum_gl=plane_sums(x[2]),
                             absmax=np.array([np.abs(x[0]).max(), np.abs(x[1]).max()]))
         print(name, "break_after", n, "t", t, "steps", steps, "total", total, "h", h, f"{time.time() - t0:.0f} s", flush=True)
 

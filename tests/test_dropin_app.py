@@ -74,9 +74,12 @@ set comment="drop-in test"
 """
 
 
-def _run(binary, workdir, outdir, threads=8):
+def _run(binary, workdir, outdir, threads=8, ngpus=None):
     os.makedirs(os.path.join(workdir, outdir), exist_ok=True)
     env = dict(os.environ, OUTPUT=outdir, OMP_NUM_THREADS=str(threads), OMP_SCHEDULE="static")
+    env.pop("PFT_NGPUS", None)
+    if ngpus:
+        env["PFT_NGPUS"] = str(ngpus)      # ONE host process cuts the block into z-slabs, one per GPU
     r = subprocess.run([binary, "Params"], cwd=workdir, env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     return r.stdout
@@ -91,10 +94,12 @@ def _compare(workdir, a, b, saved):
     assert la == lb and len(la) == saved
 
 
-def _case(tmp_path, mode, grid, final_time, saved, debug=False):
+def _case(tmp_path, mode, grid, final_time, saved, debug=False, full_grid=False):
     (tmp_path / "data").mkdir()
     shutil.copy(os.path.join(REF, "data", "spheres_positions.txt"), tmp_path / "data" / "spheres_positions.txt")
     dbg = "set debug_logfile = $OUTPUT/RK.log" if debug else ""
+    if full_grid:
+        dbg += "\ngrid full"       # intertrack.c:971-973: export the padded grid incl. ghost shell -> bcond_setup (:2511)
     (tmp_path / "Params").write_text(PARAMS.format(mode=mode, grid=grid, final_time=final_time, saved=saved, debug=dbg, xi_div=grid))
 
 
@@ -103,17 +108,21 @@ needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "intertrack_
 
 @needs_ref
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "obj")), reason="reference objects only exist in the build container")
-@pytest.mark.parametrize("mode,debug", [(0, False), (1, True)])
-def test_dropin_app_on_emulation(tmp_path, emu_lib, mode, debug):
+@pytest.mark.parametrize("mode,debug,ngpus,full_grid", [(0, False, None, False), (1, True, None, False), (0, False, 2, False), (1, True, 3, False),
+                                                        (0, False, None, True), (1, False, 2, True)])
+def test_dropin_app_on_emulation(tmp_path, emu_lib, mode, debug, ngpus, full_grid):
+    """debug=True installs the reference's Service_Callback (RKService: per-step log), ngpus drives several
+    emulated devices from the one process (worker threads, peer-memory protocol), full_grid makes the driver
+    export the ghost shell too (bcond_setup of the plug-in -> pft_equation_bcond_host)"""
     objs = [os.path.join(REF, "obj", o) for o in ("intertrack_b200.o", "rk_mpi_sa_b200.o", "equation_b200.o")]
     objs += [o for o in glob.glob(os.path.join(REF, "obj", "*.o"))
              if os.path.basename(o).split(".")[0] in ("pparser", "cparser", "evsubst", "mprintf", "ee_wrapper", "exp_all", "_AVS", "shim_rt")
              or os.path.basename(o).startswith("str_")]
     exe = str(tmp_path / "intertrack_b200_emu")
     subprocess.run(["gcc", "-fopenmp", "-o", exe, *objs, emu_lib, "-Wl,-rpath," + os.path.dirname(emu_lib), "-lstdc++", "-lm"], check=True)
-    _case(tmp_path, mode, 24, 0.6, 3, debug)
+    _case(tmp_path, mode, 24, 0.6, 3, debug, full_grid)
     _run(os.path.join(REF, "intertrack_ref"), str(tmp_path), "OUT_ref")
-    _run(exe, str(tmp_path), "OUT_b200")
+    _run(exe, str(tmp_path), "OUT_b200", ngpus=ngpus)
     _compare(str(tmp_path), "OUT_ref", "OUT_b200", 3)
 
 
@@ -129,4 +138,23 @@ def test_dropin_app_on_gpu(tmp_path, mode, grid, final_time, debug):
     _case(tmp_path, mode, grid, final_time, 4, debug)
     _run(os.path.join(REF, "intertrack_ref"), str(tmp_path), "OUT_ref", threads=os.cpu_count() or 8)
     _run(exe, str(tmp_path), "OUT_b200")
+    _compare(str(tmp_path), "OUT_ref", "OUT_b200", 4)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("ngpus,mode,grid,final_time,debug", [(2, 1, 100, 3.0, False), (2, 0, 100, 2.0, True), (4, 1, 100, 3.0, False), (8, 1, 200, 0.5, False)])
+def test_dropin_app_multi_gpu(tmp_path, ngpus, mode, grid, final_time, debug):
+    """the UNMODIFIED reference driver on 2/4/8 B200s of one box through RK_MPI_SA_solve: PFT_NGPUS=n makes the
+    one host process cut its block into n z-slabs (intertrack.c:1780-1787) -- snapshots byte-identical to the
+    reference application's, logged step counts equal.  Skipped on boxes with fewer GPUs."""
+    import torch
+    if torch.cuda.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    exe = os.path.join(REF, "intertrack_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/intertrack_b200 not built")
+    _case(tmp_path, mode, grid, final_time, 4, debug)
+    _run(os.path.join(REF, "intertrack_ref"), str(tmp_path), "OUT_ref", threads=os.cpu_count() or 8)
+    _run(exe, str(tmp_path), "OUT_b200", ngpus=ngpus)
     _compare(str(tmp_path), "OUT_ref", "OUT_b200", 4)

@@ -138,6 +138,8 @@ def test_bench_line_schema_dry_run(emu_lib, extra):
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"]) and d["roofline"]["bound"] == "hbm"
     assert len(d["roofline"]["per_stage"]) == 5 and [s["bytes_per_cell"] for s in d["roofline"]["per_stage"]] == [40, 56, 40, 72, 88]
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
-    # 5 stage kernels per attempt: 4 + the speculative stage 1 of the next step
+    # 5 stage launches per attempt (stage 1 returns at once while K1 is still valid); the adaptive run may enqueue
+    # attempts beyond the budgeted end only up to the budget itself
     assert d["gpu_launches"] == 5 * 3
+    assert len(d["device_ms_regions"]) == 7 and "parity" in d and "also" in d
     assert ("fixed step" in d["config"]["mode"]) == bool(extra)
