@@ -122,6 +122,8 @@ typedef struct {
 	                            pow(); 0: the host supplies pow() once per attempt (twin unavailable or PFT_FLAG_HOST_POW) */
 	int    runahead;         /* attempts the host keeps enqueued ahead of the device */
 	long   noop_launches;    /* stage launches that found the integration already finished (run-ahead tail) */
+	int    kernel_generation;/* of the dominant stage kernel: 0 merson_stage, 1 merson_stage_tma, 2 merson_stage_v2 */
+	int    rows_per_thread;  /* cells per thread of that kernel */
 } pft_stats;
 
 const char *pft_last_error(void);

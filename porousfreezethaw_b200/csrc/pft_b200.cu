@@ -18,6 +18,7 @@
 #include "../../include/pft_b200.h"
 #include "pft_kernels.cuh"
 #include "pft_kernels_tma.cuh"
+#include "pft_kernels_v2.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -155,6 +156,18 @@ enum { A_X = 0, A_K1, A_A3, A_K3, A_K4, A_XN, A_COUNT };   // array pairs (u,p);
 
 struct StageTimer { cudaEvent_t a, b; int stage; };
 
+// how one stage is launched.  ver 0: merson_stage (per-thread loads), 1: merson_stage_tma, 2: merson_stage_v2
+struct StageCfg {
+	int ver, R;           // kernel generation; cells per thread (rows)
+	bool nobar;           // v2, stages 1 and 3: no CTA barrier in the plane loop (the last warp to leave a plane refills its buffer)
+	bool fixed;           // v2: an instantiation with this tile shape as compile-time constants exists
+	int TX, TY;           // threads; the tile is TX x (TY*R) cells
+	int bx, by, as;       // TMA box (TX+4) x (TY*R+2) and the doubles per array buffer
+	int nzc, zc;          // z-chunks and planes per chunk
+	dim3 grid, block;
+	size_t smem;
+};
+
 struct pft_solver {
 	pft_case cs;
 	unsigned flags;
@@ -163,9 +176,7 @@ struct pft_solver {
 	Geom g;
 	int model;            // 0,1,2
 	bool heat;
-	int TX, TY, nzc;
-	dim3 grid, block;
-	size_t smem;
+	StageCfg cfg[5];      // launch geometry and kernel variant of each of the five stages
 	long long field;      // doubles per field array
 	double *arr[A_COUNT][2];   // [pair][u|p]
 	double *gl;
@@ -206,10 +217,6 @@ struct pft_solver {
 	pft_group *group;                          // member of an in-process group (pft_group_*)
 	// TMA path (heat modes): one tensor map per array, box = tile + halo ring
 	bool use_tma;
-	CUtensorMap tmap[A_COUNT][2];
-	CUtensorMap tmap_gl;
-	int bx, by, as;
-	size_t smem_tma[5];
 	// launch arguments of the five stages: independent of the step length and of earlier outcomes (pft_ctl.h)
 	bool params_ok;
 	KParams kp[5];
@@ -290,7 +297,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 3-D tensor map over one field array: (px, n2, n3+2) doubles, box (bx, by, 1)
-static int make_tensor_map(pft_solver *s, CUtensorMap *m, double *base)
+static int make_tensor_map(pft_solver *s, CUtensorMap *m, double *base, int bx, int by)
 {
 	static encode_tiled_fn encode = nullptr;
 	if (!encode) {
@@ -303,11 +310,11 @@ static int make_tensor_map(pft_solver *s, CUtensorMap *m, double *base)
 	const Geom &g = s->g;
 	cuuint64_t dim[3] = {(cuuint64_t)g.px, (cuuint64_t)g.n2, (cuuint64_t)(g.n3 + 2)};
 	cuuint64_t strides[2] = {(cuuint64_t)g.px * sizeof(double), (cuuint64_t)g.plane * sizeof(double)};
-	cuuint32_t box[3] = {(cuuint32_t)s->bx, (cuuint32_t)s->by, 1u};
+	cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1u};
 	cuuint32_t estr[3] = {1u, 1u, 1u};
 	CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dim, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
 	                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-	if (r != CUDA_SUCCESS) return fail(PFT_ECUDA, "cuTensorMapEncodeTiled failed (%d) for box %dx%d", (int)r, s->bx, s->by);
+	if (r != CUDA_SUCCESS) return fail(PFT_ECUDA, "cuTensorMapEncodeTiled failed (%d) for box %dx%d", (int)r, bx, by);
 	return 0;
 }
 
@@ -364,19 +371,24 @@ static const PowGate &pow_gate()
 // ------------------------------------------------------------------------------------------
 // stage launch
 
-template <int STAGE, int MODEL, bool HEAT>
-static cudaError_t launch_t(pft_solver *s, const KParams &kp)
+template <class K, class PARAMS>
+static cudaError_t launch_kernel(pft_solver *s, K fn, bool *attr_set_dev, const StageCfg &cf, const PARAMS &kp)
 {
-	auto fn = merson_stage<STAGE, MODEL, HEAT>;
-	static bool attr_set_dev[64] = {};        // the attribute is per device (and per template instance)
-	bool &attr_set = attr_set_dev[s->device & 63];
+	bool &attr_set = attr_set_dev[s->device & 63];        // the attribute is per device (and per template instance)
 	if (!attr_set) {
-		cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
 		if (e != cudaSuccess) return e;
 		attr_set = true;
 	}
-	PFT_LAUNCH_PDL(s->pdl, fn, s->grid, s->block, s->smem, s->stream, kp);
+	PFT_LAUNCH_PDL(s->pdl, fn, cf.grid, cf.block, cf.smem, s->stream, kp);
 	return cudaGetLastError();
+}
+
+template <int STAGE, int MODEL, bool HEAT>
+static cudaError_t launch_t(pft_solver *s, const KParams &kp)
+{
+	static bool attr[64] = {};
+	return launch_kernel(s, merson_stage<STAGE, MODEL, HEAT>, attr, s->cfg[STAGE - 1], kp);
 }
 
 template <int STAGE>
@@ -390,21 +402,50 @@ static cudaError_t launch_stage_t(pft_solver *s, const KParams &kp)
 template <int STAGE, int MODEL>
 static cudaError_t launch_tma_t(pft_solver *s, const TmaParams &kp)
 {
-	auto fn = merson_stage_tma<STAGE, MODEL>;
-	static bool attr_set_dev[64] = {};        // the attribute is per device (and per template instance)
-	bool &attr_set = attr_set_dev[s->device & 63];
-	if (!attr_set) {
-		cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-		if (e != cudaSuccess) return e;
-		attr_set = true;
+	static bool attr[64] = {};
+	return launch_kernel(s, merson_stage_tma<STAGE, MODEL>, attr, s->cfg[STAGE - 1], kp);
+}
+
+// second-generation kernel: R cells per thread, optional compile-time tile shape, optional barrier-free plane loop
+template <int STAGE, int MODEL, int R, int CTX, int CTY, bool NOBAR>
+static cudaError_t launch_v2_t(pft_solver *s, const TmaParams &kp)
+{
+	static bool attr[64] = {};
+	return launch_kernel(s, merson_stage_v2<STAGE, MODEL, R, CTX, CTY, NOBAR>, attr, s->cfg[STAGE - 1], kp);
+}
+
+// the tile shapes that exist as compile-time instantiations (threads TX x TY; cells TX x TY*R)
+#define PFT_FIXED_TX 50
+#define PFT_FIXED_TY 5
+static bool have_fixed_shape(int R, int TX, int TY) { return (R == 1 || R == 2) && TX == PFT_FIXED_TX && TY == PFT_FIXED_TY; }
+
+template <int STAGE, int MODEL, int R>
+static cudaError_t launch_v2_shape(pft_solver *s, const TmaParams &kp)
+{
+	const StageCfg &cf = s->cfg[STAGE - 1];
+	constexpr bool CAN_NOBAR = (STAGE == 1 || STAGE == 3);
+	if (cf.fixed) {
+		if (CAN_NOBAR && cf.nobar) return launch_v2_t<STAGE, MODEL, R, PFT_FIXED_TX, PFT_FIXED_TY, CAN_NOBAR>(s, kp);
+		return launch_v2_t<STAGE, MODEL, R, PFT_FIXED_TX, PFT_FIXED_TY, false>(s, kp);
 	}
-	PFT_LAUNCH_PDL(s->pdl, fn, s->grid, s->block, s->smem_tma[STAGE - 1], s->stream, kp);
-	return cudaGetLastError();
+	if (CAN_NOBAR && cf.nobar) return launch_v2_t<STAGE, MODEL, R, 0, 0, CAN_NOBAR>(s, kp);
+	return launch_v2_t<STAGE, MODEL, R, 0, 0, false>(s, kp);
+}
+
+template <int STAGE, int MODEL>
+static cudaError_t launch_v2_rows(pft_solver *s, const TmaParams &kp)
+{
+	return s->cfg[STAGE - 1].R == 2 ? launch_v2_shape<STAGE, MODEL, 2>(s, kp) : launch_v2_shape<STAGE, MODEL, 1>(s, kp);
 }
 
 template <int STAGE>
 static cudaError_t launch_stage_tma_t(pft_solver *s, const TmaParams &kp)
 {
+	if (s->cfg[STAGE - 1].ver == 2) {
+		if (s->model == 2) return launch_v2_rows<STAGE, 2>(s, kp);
+		if (s->model == 0) return launch_v2_rows<STAGE, 0>(s, kp);
+		return launch_v2_rows<STAGE, 1>(s, kp);
+	}
 	if (s->model == 2) return launch_tma_t<STAGE, 2>(s, kp);
 	if (s->model == 0) return launch_tma_t<STAGE, 0>(s, kp);
 	return launch_tma_t<STAGE, 1>(s, kp);
@@ -417,7 +458,7 @@ static void fill_peer_args(pft_solver *s, PeerArgs *pr, int stage)
 	const size_t plane_b = (size_t)s->g.plane * sizeof(double);
 	const int outs[5] = {A_K1, A_A3, A_K3, A_K4, -1};
 	pr->rank = r; pr->nranks = R;
-	pr->nzc = s->nzc;
+	pr->nzc = s->cfg[stage - 1].nzc;
 	pr->my_flags = ((SyncBlock *)s->slab)->halo_flag;
 	pr->tickets = s->halo_tickets;
 	pr->wait_lo = (r > 0); pr->wait_hi = (r < R - 1);
@@ -443,13 +484,15 @@ static void fill_peer_args(pft_solver *s, PeerArgs *pr, int stage)
 
 // The argument blocks of the five stages.  Built once (and again when the transport changes):
 // nothing in them depends on the step length, the time level or the outcome of an attempt.
-static void build_params(pft_solver *s)
+static int build_params(pft_solver *s)
 {
 	const bool separate_nccl = s->cs.nranks > 1 && !s->p2p;
 	for (int stage = 1; stage <= 5; stage++) {
+		const StageCfg &cf = s->cfg[stage - 1];
 		KParams &kp = s->kp[stage - 1];
 		kp.c = s->c;
 		kp.g = s->g;
+		kp.g.zc = cf.zc;
 		StageArgs &a = kp.a;
 		memset(&a, 0, sizeof a);
 		a.ctl = s->ctl;
@@ -463,32 +506,36 @@ static void build_params(pft_solver *s)
 		const int outs[5] = {A_K1, A_A3, A_K3, A_K4, A_XN};
 		a.ou = s->arr[outs[stage - 1]][0]; a.op = s->arr[outs[stage - 1]][1];
 		if (s->p2p) fill_peer_args(s, &a.pr, stage);
-		else a.pr.nzc = s->nzc;
+		else a.pr.nzc = cf.nzc;
 		a.pr.rank = s->cs.rank;
 		a.pr.nranks = s->p2p ? s->cs.nranks : 1;       // the in-kernel error-max exchange exists on the peer path only
 		if (stage == 5) {
 			a.slot = s->slot_dev;
 			a.tab = s->tab_dev;
-			a.nblocks = s->grid.x * s->grid.y * s->grid.z;
+			a.nblocks = cf.grid.x * cf.grid.y * cf.grid.z;
 			a.fin_mode = separate_nccl ? FIN_STORE_LOCAL : (s->dev_pow ? FIN_DECIDE : FIN_PUBLISH_EPS);
 		}
 		if (s->use_tma) {
 			TmaParams &tp = s->tp[stage - 1];
 			tp.c = kp.c; tp.g = kp.g; tp.a = kp.a;
-			tp.bx = s->bx; tp.by = s->by; tp.as = s->as;
-			// array order of a stage: p-type arrays, u-type arrays, gl (pft_kernels_tma.cuh, stage_np)
+			tp.bx = cf.bx; tp.by = cf.by; tp.as = cf.as; tp.tx = cf.TX; tp.ty = cf.TY;
+			// array order of a stage: p-type arrays, u-type arrays, gl (pft_kernels_tma.cuh, stage_np); one tensor
+			// map per array with this stage's box
 			const int src[5][4] = {{A_X, -1, -1, -1}, {A_X, A_K1, -1, -1}, {A_A3, -1, -1, -1}, {A_X, A_K1, A_K3, -1}, {A_X, A_K1, A_K3, A_K4}};
 			const int np = stage_np(stage);
-			for (int m = 0; m < np; m++) {
-				tp.maps[m] = s->tmap[src[stage - 1][m]][1];
-				tp.maps[np + m] = s->tmap[src[stage - 1][m]][0];
+			int rc = 0;
+			for (int m = 0; m < np && !rc; m++) {
+				rc = make_tensor_map(s, &tp.maps[m], s->arr[src[stage - 1][m]][1], cf.bx, cf.by);
+				if (!rc) rc = make_tensor_map(s, &tp.maps[np + m], s->arr[src[stage - 1][m]][0], cf.bx, cf.by);
 			}
-			tp.maps[2 * np] = s->tmap_gl;
-			tp.xalt[0] = s->tmap[A_XN][1];
-			tp.xalt[1] = s->tmap[A_XN][0];
+			if (!rc) rc = make_tensor_map(s, &tp.maps[2 * np], s->gl, cf.bx, cf.by);
+			if (!rc) rc = make_tensor_map(s, &tp.xalt[0], s->arr[A_XN][1], cf.bx, cf.by);
+			if (!rc) rc = make_tensor_map(s, &tp.xalt[1], s->arr[A_XN][0], cf.bx, cf.by);
+			if (rc) return rc;
 		}
 	}
 	s->params_ok = true;
+	return 0;
 }
 
 static int exchange_pair(pft_solver *s, double *u, double *p);
@@ -496,7 +543,7 @@ static int exchange_pair(pft_solver *s, double *u, double *p);
 // one stage launch.  standalone != nullptr: a single right-hand-side evaluation outside the time loop
 static int launch_stage(pft_solver *s, int stage, const double *standalone_dir = nullptr)
 {
-	if (!s->params_ok) build_params(s);
+	if (!s->params_ok) { int rc_ = build_params(s); if (rc_) return rc_; }
 	StageTimer tm{};
 	if (s->profile) {
 		cudaEventCreate(&tm.a); cudaEventCreate(&tm.b); tm.stage = stage;
@@ -509,7 +556,7 @@ static int launch_stage(pft_solver *s, int stage, const double *standalone_dir =
 		if (standalone_dir) {
 			alone = *tp;
 			memset(&alone.a.pr, 0, sizeof alone.a.pr);
-			alone.a.pr.nzc = s->nzc; alone.a.pr.nranks = 1;
+			alone.a.pr.nzc = s->cfg[stage - 1].nzc; alone.a.pr.nranks = 1;
 			alone.a.standalone = 1; alone.a.standalone_cur = s->cur; alone.a.dir_standalone = *standalone_dir;
 			tp = &alone;
 		}
@@ -526,7 +573,7 @@ static int launch_stage(pft_solver *s, int stage, const double *standalone_dir =
 		if (standalone_dir) {
 			alone = *kp;
 			memset(&alone.a.pr, 0, sizeof alone.a.pr);
-			alone.a.pr.nzc = s->nzc; alone.a.pr.nranks = 1;
+			alone.a.pr.nzc = s->cfg[stage - 1].nzc; alone.a.pr.nranks = 1;
 			alone.a.standalone = 1; alone.a.standalone_cur = s->cur; alone.a.dir_standalone = *standalone_dir;
 			kp = &alone;
 		}
@@ -738,30 +785,60 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	s->padded = (long long)PFT_NVAR * s->N1 * s->N2 * s->N3;
 
 	s->use_tma = s->heat && !(flags & PFT_FLAG_LEGACY_LOADS) && !env_int("PFT_LEGACY", 0);
-	int max_threads = env_int("PFT_THREADS", 256);     // two or three CTAs per SM overlap each other's barrier waits
-	if (max_threads < 32) max_threads = 32;
-	if (max_threads > 512) max_threads = 512;
-	if (s->use_tma && max_threads > 256) max_threads = 256;      // __launch_bounds__ of the TMA kernels
-	choose_tile(cs->n1, cs->n2, max_threads, &s->TX, &s->TY);
-	if (env_int("PFT_TX", 0) > 0) s->TX = env_int("PFT_TX", 0);
-	if (env_int("PFT_TY", 0) > 0) s->TY = env_int("PFT_TY", 0);
-	if (s->TX & 1) s->TX++;                  // tile origins must be even (TMA inner-offset alignment)
-	if (s->TX * s->TY > (s->use_tma ? 256 : 512) || s->TX * s->TY < 2 * s->TX + 2 * s->TY) {
-		int tx_ = s->TX, ty_ = s->TY;
-		delete s;
-		return fail(PFT_EINVAL, "tile %dx%d unusable (needs TX*TY <= 512 and enough threads for the halo ring)", tx_, ty_);
-	}
-	int tiles_xy = ((cs->n1 + s->TX - 1) / s->TX) * ((cs->n2 + s->TY - 1) / s->TY);
-	s->nzc = choose_chunks(tiles_xy, cs->n3, prop.multiProcessorCount);
-	if (env_int("PFT_ZCHUNKS", 0) > 0) s->nzc = std::min(cs->n3, env_int("PFT_ZCHUNKS", 0));
-	g.zc = (cs->n3 + s->nzc - 1) / s->nzc;
-	s->nzc = (cs->n3 + g.zc - 1) / g.zc;
-	s->grid = dim3((cs->n1 + s->TX - 1) / s->TX, (cs->n2 + s->TY - 1) / s->TY, s->nzc);
-	s->block = dim3(s->TX, s->TY, 1);
 	{
-		int NF = s->heat ? 3 : 1;
-		size_t ts = (size_t)(s->TX + 2) * (s->TY + 2);
-		s->smem = (2 * NF * ts) * sizeof(double);
+		// per-stage kernel variant: PFT_KERNEL = 1 | 2 (generation), PFT_ROWS = cells per thread, one digit per stage
+		// ("2" or "21211"), PFT_NOBAR = 0 | 1 (stages 1 and 3 without CTA barrier), PFT_FIXED_SHAPE = 0 | 1
+		const int kver = s->use_tma ? std::max(1, std::min(2, env_int("PFT_KERNEL", 2))) : 0;
+		const char *rows = getenv("PFT_ROWS");
+		const int nrows = (rows && *rows) ? (int)strlen(rows) : 0;
+		const bool want_nobar = env_int("PFT_NOBAR", 1) != 0, want_fixed = env_int("PFT_FIXED_SHAPE", 1) != 0;
+		for (int st = 0; st < 5; st++) {
+			StageCfg &cf = s->cfg[st];
+			cf.ver = kver;
+			cf.R = 1;
+			if (kver == 2 && nrows > 0) cf.R = std::max(1, std::min(2, (int)(rows[std::min(st, nrows - 1)] - '0')));
+			cf.nobar = kver == 2 && want_nobar && (st == 0 || st == 2);
+			int max_threads = env_int("PFT_THREADS", 256);     // two or three CTAs per SM overlap each other's barrier waits
+			if (max_threads < 32) max_threads = 32;
+			if (max_threads > 512) max_threads = 512;
+			if (s->use_tma && max_threads > 256) max_threads = 256;      // __launch_bounds__ of the TMA kernels
+			choose_tile(cs->n1, (cs->n2 + cf.R - 1) / cf.R, max_threads, &cf.TX, &cf.TY);
+			if (env_int("PFT_TX", 0) > 0) cf.TX = env_int("PFT_TX", 0);
+			if (env_int("PFT_TY", 0) > 0) cf.TY = env_int("PFT_TY", 0);
+			if (cf.TX & 1) cf.TX++;                  // tile origins must be even (TMA inner-offset alignment)
+			if (cf.R > 1 && cf.TX * cf.TY < 2 * cf.TX + 2 * cf.TY * cf.R) cf.R = 1;    // a forced tile too small for the taller ring
+			if (cf.TX * cf.TY > (s->use_tma ? 256 : 512) || cf.TX * cf.TY < 2 * cf.TX + 2 * cf.TY * cf.R) {
+				int tx_ = cf.TX, ty_ = cf.TY;
+				delete s;
+				return fail(PFT_EINVAL, "tile %dx%d unusable (needs TX*TY <= 512 and enough threads for the halo ring)", tx_, ty_);
+			}
+			cf.fixed = kver == 2 && want_fixed && have_fixed_shape(cf.R, cf.TX, cf.TY);
+			const int rows_t = cf.TY * cf.R;
+			const int tiles_xy = ((cs->n1 + cf.TX - 1) / cf.TX) * ((cs->n2 + rows_t - 1) / rows_t);
+			cf.nzc = choose_chunks(tiles_xy, cs->n3, prop.multiProcessorCount);
+			if (env_int("PFT_ZCHUNKS", 0) > 0) cf.nzc = std::min(cs->n3, env_int("PFT_ZCHUNKS", 0));
+			cf.zc = (cs->n3 + cf.nzc - 1) / cf.nzc;
+			cf.nzc = (cs->n3 + cf.zc - 1) / cf.zc;
+			cf.grid = dim3((cs->n1 + cf.TX - 1) / cf.TX, (cs->n2 + rows_t - 1) / rows_t, cf.nzc);
+			if (kver == 2) cf.block = dim3(cf.TX * cf.TY, 1, 1);
+			else cf.block = dim3(cf.TX, cf.TY, 1);
+			if (!s->use_tma) {
+				int NF = s->heat ? 3 : 1;
+				size_t ts = (size_t)(cf.TX + 2) * (cf.TY + 2);
+				cf.smem = (2 * NF * ts) * sizeof(double);
+				cf.bx = cf.by = cf.as = 0;
+			} else {
+				cf.bx = cf.TX + 4;                   // box starts at x = i0-2 (16-byte aligned inner offset), TX is even
+				cf.by = rows_t + 2;
+				cf.as = (cf.bx * cf.by + 15) & ~15;  // each array buffer starts 128-byte aligned
+				const int na = 2 * stage_np(st + 1) + 1;
+				const bool form = !(st == 0 || st == 2);
+				const int ntile = kver == 2 ? 6 : 4;  // state tiles: double buffered (v1), one per raw buffer (v2)
+				cf.smem = ((size_t)TMA_STAGES * na * cf.as + (form ? ntile * (size_t)cf.as : 0)) * sizeof(double);
+				if (cf.smem > 225 * 1024) { size_t b_ = cf.smem; int tx_ = cf.TX, ty_ = cf.TY; delete s; return fail(PFT_EINVAL, "tile %dx%d needs %zu bytes of shared memory", tx_, ty_, b_); }
+			}
+		}
+		g.zc = s->cfg[0].zc;
 	}
 
 	CUS(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -790,26 +867,6 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	CUS(cudaMalloc(&s->halo_tickets, 2 * sizeof(unsigned int)));
 	CUS(cudaMemsetAsync(s->halo_tickets, 0, 2 * sizeof(unsigned int), s->stream));
 
-	if (s->use_tma) {
-		s->bx = s->TX + 4;                   // box starts at x = i0-2 (16-byte aligned inner offset), TX is even
-		s->by = s->TY + 2;
-		s->as = (s->bx * s->by + 15) & ~15;  // each array buffer starts 128-byte aligned
-		size_t worst = 0;
-		for (int st = 1; st <= 5; st++) {
-			int na = 2 * stage_np(st) + 1;
-			bool form = !(st == 1 || st == 3);
-			s->smem_tma[st - 1] = ((size_t)TMA_STAGES * na * s->as + (form ? 4 * (size_t)s->as : 0)) * sizeof(double);
-			worst = std::max(worst, s->smem_tma[st - 1]);
-		}
-		if (worst > 225 * 1024) { pft_destroy(s); return fail(PFT_EINVAL, "tile %dx%d needs %zu bytes of shared memory", s->TX, s->TY, worst); }
-		for (int a = 0; a < A_COUNT; a++)
-			for (int q = 0; q < 2; q++) {
-				int rc = make_tensor_map(s, &s->tmap[a][q], s->arr[a][q]);
-				if (rc) { pft_destroy(s); return rc; }
-			}
-		int rc = make_tensor_map(s, &s->tmap_gl, s->gl);
-		if (rc) { pft_destroy(s); return rc; }
-	}
 	CUS(cudaMalloc(&s->ctl, sizeof(StepCtl)));
 	CUS(cudaMemsetAsync(s->ctl, 0, sizeof(StepCtl), s->stream));
 	CUS(cudaHostAlloc(&s->ctl_host, sizeof(StepCtl), cudaHostAllocDefault));
@@ -828,8 +885,12 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	CUS(cudaStreamSynchronize(s->stream));
 
 	memset(&s->st, 0, sizeof s->st);
-	s->st.tile_x = s->TX; s->st.tile_y = s->TY; s->st.z_chunk = g.zc; s->st.threads = s->TX * s->TY;
-	s->st.grid_blocks = s->grid.x * s->grid.y * s->grid.z;
+	{
+		const StageCfg &cf = s->cfg[4];          // the dominant stage
+		s->st.tile_x = cf.TX; s->st.tile_y = cf.TY * cf.R; s->st.z_chunk = cf.zc; s->st.threads = cf.TX * cf.TY;
+		s->st.grid_blocks = cf.grid.x * cf.grid.y * cf.grid.z;
+		s->st.kernel_generation = cf.ver; s->st.rows_per_thread = cf.R;
+	}
 	s->st.bytes_per_field = (long)fb;
 	s->st.device_pow = s->dev_pow ? 1 : 0;
 	s->st.runahead = s->depth;
@@ -1270,7 +1331,7 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 	if (sys->delta <= 0) { fail(PFT_EINVAL, "delta <= 0"); return PFT_SOLVE_BADSYSTEM; }        // hybrid2.c:286
 	if (cudaSetDevice(s->device) != cudaSuccess) return fail(PFT_ECUDA, "cudaSetDevice failed");
 	if (s->cs.nranks > 1 && !s->p2p && !s->have_comm) return fail(PFT_ESTATE, "nranks > 1 but pft_comm_init was not called");
-	if (!s->params_ok) build_params(s);
+	if (!s->params_ok && build_params(s)) return PFT_ECUDA;
 
 	const bool nccl_mode = s->cs.nranks > 1 && !s->p2p;
 	const bool host_pow = !s->dev_pow;
@@ -1571,5 +1632,6 @@ extern "C" int pft_reset_stats(pft_solver *s)
 	s->st.tile_x = keep.tile_x; s->st.tile_y = keep.tile_y; s->st.z_chunk = keep.z_chunk;
 	s->st.threads = keep.threads; s->st.grid_blocks = keep.grid_blocks; s->st.bytes_per_field = keep.bytes_per_field;
 	s->st.device_pow = keep.device_pow; s->st.runahead = keep.runahead;
+	s->st.kernel_generation = keep.kernel_generation; s->st.rows_per_thread = keep.rows_per_thread;
 	return 0;
 }

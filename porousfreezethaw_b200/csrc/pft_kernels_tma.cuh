@@ -43,6 +43,7 @@ struct alignas(64) TmaParams {
 	StageArgs a;
 	int bx, by;                          // box extents: bx = TX+4 (TX even; the box starts at the even x = i0-2), by = TY+2
 	int as;                              // doubles per array buffer (bx*by rounded up to 16 = 128 B)
+	int tx, ty;                          // merson_stage_v2 (1-D thread block): threads per tile row / thread rows
 };
 
 // number of p-type (and u-type) arrays stage S stages through shared memory
@@ -177,6 +178,29 @@ __device__ __forceinline__ void stage_output(const OutPtrs &a, double hb, const 
 		const double vp = xp + hb * (0.5 * (k1p + dp) + 2.0 * k4p);                           // :667
 		const double vu = xu + hb * (0.5 * (k1u + du) + 2.0 * k4u);
 		store_out<true>(a, o, col, k, n3, vu, vp);
+	}
+}
+
+// the values a stage stores for one cell (the fused combination that follows the stage), and the error estimate
+template <int STAGE>
+__device__ __forceinline__ void stage_values(double hb, const double *rb, int AS, int IU, int cs, double du, double dp,
+                                             double &emax, int &nonfinite, double &vu, double &vp)
+{
+	if (STAGE == 1 || STAGE == 3 || STAGE == 4) {
+		vu = du; vp = dp;
+	} else if (STAGE == 2) {
+		vp = (rb[AS + cs] + dp) * hb + rb[cs];                                                 // hybrid2.c:408
+		vu = (rb[(IU + 1) * AS + cs] + du) * hb + rb[IU * AS + cs];
+	} else {
+		const double xp = rb[cs], k1p = rb[AS + cs], k3p = rb[2 * AS + cs], k4p = rb[3 * AS + cs];
+		const double xu = rb[IU * AS + cs], k1u = rb[(IU + 1) * AS + cs], k3u = rb[(IU + 2) * AS + cs], k4u = rb[(IU + 3) * AS + cs];
+		double e = fabs(0.2 * k1p - 0.9 * k3p + 0.8 * k4p - 0.1 * dp);                          // :521
+		double eu = fabs(0.2 * k1u - 0.9 * k3u + 0.8 * k4u - 0.1 * du);
+		if (!(e <= 1.7976931348623157e308) || !(eu <= 1.7976931348623157e308)) nonfinite = 1;
+		emax = (e > emax) ? e : emax;
+		emax = (eu > emax) ? eu : emax;
+		vp = xp + hb * (0.5 * (k1p + dp) + 2.0 * k4p);                                          // :667
+		vu = xu + hb * (0.5 * (k1u + du) + 2.0 * k4u);
 	}
 }
 

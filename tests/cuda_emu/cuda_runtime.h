@@ -65,6 +65,7 @@ uint32_t tensor_load_3d(void *dst, const void *map, int x, int y, int z);   // r
 static inline void __syncthreads() { pft_emu::syncthreads(); }
 static inline void __syncwarp() { pft_emu::syncwarp(); }
 static inline void __threadfence() {}
+static inline void __threadfence_block() {}
 static inline void __threadfence_system() {}
 
 static inline int min(int a, int b) { return a < b ? a : b; }
