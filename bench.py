@@ -294,7 +294,9 @@ class Bench:
         u, p, gl = spec.initial_fields(first_row=sol.first_row, n3_local=sol.n3)
         sol.upload_interior(u, p, gl)
         if device_rasteriser:
+            t0 = time.perf_counter()
             sol.rasterise(spec.spheres)
+            self.rasterise_ms = 1e3 * (time.perf_counter() - t0)       # device rasteriser (spheres binned), incl. host-side binning and sync
         sol.sys.t, sol.sys.h = float(spec.extra.get("t0", 0.0)), spec.tau      # a restart dataset may set both
         sol.sys.steps = sol.sys.steps_total = 0
 
@@ -364,6 +366,41 @@ def parity_check(b: Bench, golden_path: str):
                 "fields": "per-plane checksums of u, p, gl: every rank its own planes, bit-exact"}
     finally:
         sol.close()
+
+
+def dropin_e2e(spec, ngpus: int, t_probe: float):
+    """End to end THROUGH THE REFERENCE'S SOLVER-MODULE ABI: RK_MPI_SA_solve(final_time, &system) of librk_b200.so with
+    the padded host array `system->x` (pageable numpy memory, page-locked by the module on first use), the chunk
+    table of intertrack.c:2149-2156 and the plug-in's host rasteriser -- exactly the calls the reference driver
+    makes.  ngpus > 1: this ONE process drives all of them (PFT_NGPUS).  The first call (page-locking, glass field
+    upload) is not timed; the second one is."""
+    from porousfreezethaw_b200.dropin import DropInRun
+    run = DropInRun(spec, ngpus)
+    try:
+        u, p, gl = spec.initial_fields()
+        w = np.zeros((3, run.N3, run.N2, run.N1))
+        for q, a in enumerate((u, p, gl)):
+            w[q, 2:-2, 2:-2, 2:-2] = a
+        del u, p, gl
+        w = w.reshape(-1)
+        run.rasterise_host(w)
+        rc = run.solve(w, 0.25 * t_probe)
+        if rc != 0:
+            raise RuntimeError(f"RK_MPI_SA_solve returned {rc}")
+        a0, s0 = run.system.steps_total, run.system.steps
+        t0 = time.perf_counter()
+        rc = run.solve(w, t_probe)
+        dt = time.perf_counter() - t0
+        if rc != 0:
+            raise RuntimeError(f"RK_MPI_SA_solve returned {rc}")
+        att, acc = run.system.steps_total - a0, run.system.steps - s0
+        rhs = 4 * att + acc
+        nbytes = 2 * spec.n3 * run.N1 * run.N2 * 8
+        return {"value": spec.cells * rhs / dt / 1e6, "unit": "Mcell-RHS/s", "gpus": ngpus, "attempts": att, "seconds": dt,
+                "h2d_bytes_per_step": nbytes / max(att, 1), "d2h_bytes_per_step": nbytes / max(att, 1),
+                "note": "one RK_MPI_SA_solve call of librk_b200.so (solver-module ABI of include/RK_MPI_SAsolver.h) on a host-resident x"}
+    finally:
+        run.close()
 
 
 def stage_profile(b: Bench, H, peak, peak_src):
@@ -462,6 +499,7 @@ def run_workload(args, name, rank, N, local, lib_path, dry, dist, torch, steps, 
         "value": value, "unit": "Mcell-RHS/s", "steps": steps, "repeats": repeats, "ms_per_step": dev_ms / steps,
         "device_ms_regions": [round(d, 4) for d in devs], "wall_ms_per_step": wall_ms / steps,
         "rhs_evals_per_attempt": rhs_per_region / steps,
+        "rasterise_ms": {"ms": round(getattr(b, "rasterise_ms", 0.0), 3), "spheres": int(len(spec.spheres)), "cells_per_gpu": int(sol.cells)},
         "roofline_step": {"achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                           "note": "algorithmic bytes of the stage kernels that did work in a timed region / its device time, per GPU (launch gaps included)"},
     }
@@ -483,6 +521,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the end-to-end figure through RK_MPI_SA_solve (e2e_dropin)")
     ap.add_argument("--variant", default="strict", choices=["strict", "fast"],
                     help="strict = IEEE association, bit-exact (default); fast = FMA contraction allowed (fields within 1e-10, no step-sequence parity)")
     ap.add_argument("--fixed-step", action="store_true",
@@ -587,6 +626,18 @@ def main():
            "note": "one solve call = upload(u, p) + K attempts + download(u, p) through the C ABI with pinned host buffers, as RK_MPI_SA_solve "
                    "with a host-resident x (gl is static and stays on the device); long_call = the same with 10 K attempts"}
 
+    # ---- the same through the reference's solver-module ABI (one host process; all GPUs it can see) ----
+    e2e_dropin = None
+    if N == 1 and not dry and not args.fixed_step and args.variant == "strict" and os.path.exists(_pftlib.RK_LIB_PATH) and not args.no_dropin:
+        e2e_dropin = []
+        t_probe = float(sol.sys.t)
+        counts = [1] + ([torch.cuda.device_count()] if torch.cuda.device_count() > 1 else [])
+        for g_ in counts:
+            try:
+                e2e_dropin.append(dropin_e2e(spec, g_, t_probe))
+            except Exception as e:
+                e2e_dropin.append({"gpus": g_, "error": repr(e)})
+
     # ---- parity of THIS workload against the unmodified reference -------------------------
     parity = None
     gpath = os.path.join(ROOT, "tests", "golden", f"partial_{spec.name}.npz")
@@ -647,6 +698,8 @@ def main():
             "wall_ms_per_step": frag["wall_ms_per_step"],
             "host_loop_ms_per_step": {"per_rank[asleep, launching, device]": hw},
             "roofline_step": frag["roofline_step"],
+            "e2e_dropin": e2e_dropin,
+            "rasterise_ms": frag["rasterise_ms"],
             "parity": parity,
             "also": also,
         }

@@ -107,25 +107,27 @@ def load(path: str | None = None) -> C.CDLL:
     return lib
 
 
-_rk = None
+_rk: dict[str, C.CDLL] = {}
 
 
-def load_rk() -> C.CDLL:
+def load_rk(path: str | None = None) -> C.CDLL:
     """librk_b200.so: the drop-in host objects (solver module + host side of the model plug-in)."""
-    global _rk
-    if _rk is None:
-        if not os.path.exists(RK_LIB_PATH):
-            raise RuntimeError(f"{RK_LIB_PATH} not found (make -C porousfreezethaw_b200/csrc)")
-        load()                      # libpft_b200.so first: librk links against it
-        _rk = C.CDLL(RK_LIB_PATH)
-        _rk.pft_equation_rasterise_host.argtypes = [C.POINTER(PftCase), _dp, C.c_int, _dp]
-    return _rk
+    path = path or RK_LIB_PATH
+    if path not in _rk:
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not found (make -C porousfreezethaw_b200/csrc)")
+        if path == RK_LIB_PATH:
+            load()                  # libpft_b200.so first: librk links against it
+        lib = C.CDLL(path)
+        lib.pft_equation_rasterise_host.argtypes = [C.POINTER(PftCase), _dp, C.c_int, _dp]
+        _rk[path] = lib
+    return _rk[path]
 
 
-def rasterise_host(case: PftCase, spheres_raw, solution_padded) -> None:
+def rasterise_host(case: PftCase, spheres_raw, solution_padded, rk_path: str | None = None) -> None:
     """the plug-in's host rasteriser (libm tanh, bit-identical to equation.c:474-529): gl of a padded array"""
     import numpy as np
     s = np.ascontiguousarray(spheres_raw, dtype=np.float64).reshape(-1, 3)
-    rc = load_rk().pft_equation_rasterise_host(C.byref(case), s.ctypes.data_as(_dp), s.shape[0], solution_padded.ctypes.data_as(_dp))
+    rc = load_rk(rk_path).pft_equation_rasterise_host(C.byref(case), s.ctypes.data_as(_dp), s.shape[0], solution_padded.ctypes.data_as(_dp))
     if rc:
         raise RuntimeError(f"pft_equation_rasterise_host failed ({rc})")

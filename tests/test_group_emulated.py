@@ -85,3 +85,30 @@ def test_group_break_by_callback(emu_lib):
         parity.assert_fields(case, got, x, True, "after breaks")
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("ngpus,mode", [(1, 0), (2, 1), (3, 0)])
+def test_solver_module_abi_from_python(emu_lib, ngpus, mode):
+    """RK_MPI_SA_init / RK_MPI_SA_solve of librk (the reference's solver-module ABI) driven the way intertrack.c
+    drives it -- chunk table of x-rows, meta_f, host-resident padded x updated in place -- on 1..3 emulated
+    devices (PFT_NGPUS): state and fields bit-identical to the oracle; the static glass field goes up once"""
+    import os
+    from porousfreezethaw_b200.dropin import DropInRun
+    rk_emu = os.path.join(os.path.dirname(emu_lib), "librk_b200_emu.so")
+    spec = cases.small_case(12, 10, 16, calc_mode=mode)
+    case, orc, w = parity.make(spec)
+    x = w.copy()
+    s = orc.new_system(t=0.0, h=spec.tau, h_min=spec.tau_min, delta=spec.delta)
+    work = np.zeros(5 * x.size)
+    run = DropInRun(spec, ngpus=ngpus, rk_path=rk_emu)
+    try:
+        xh = w.copy()
+        for T in (3.0, 7.0, 7.5):
+            assert orc.solve(s, x, T, work) == 0
+            assert run.solve(xh, T) == 0
+            sy = run.system
+            assert (sy.t, sy.h, sy.steps, sy.steps_total) == (s.t, s.h, s.steps, s.steps_total)
+            assert np.array_equal(xh, x) or np.array_equal(case.interior(xh), case.interior(x))
+        parity.assert_fields(case, xh, x, True, "through RK_MPI_SA_solve")
+    finally:
+        run.close()

@@ -29,7 +29,7 @@ rows = []
 for name, env in CONFIGS:
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", WORK, "--steps", "40", "--warmup", "10", "--repeats", "3",
-                        "--also", "none", "--no-cpu-baseline", "--no-parity", "--profile-steps", "20"], capture_output=True, text=True, env=e, cwd=ROOT)
+                        "--also", "none", "--no-cpu-baseline", "--no-parity", "--no-dropin", "--profile-steps", "20"], capture_output=True, text=True, env=e, cwd=ROOT)
     line = [l for l in r.stdout.splitlines() if l.startswith("{")]
     if r.returncode or not line:
         print(f"{name:32s} FAILED rc={r.returncode} {r.stderr[-300:]!r}", flush=True)
