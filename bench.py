@@ -349,6 +349,11 @@ def parity_check(b: Bench, golden_path: str):
         for q, a in enumerate((u, p, gl)):
             w[q, 2:-2, 2:-2, 2:-2] = a
         w = w.reshape(-1)
+        try:      # torchrun exports OMP_NUM_THREADS=1: give the host rasteriser this rank's share of the cores
+            import ctypes
+            ctypes.CDLL("libgomp.so.1", mode=ctypes.RTLD_GLOBAL).omp_set_num_threads(max(1, (os.cpu_count() or 1) // max(b.N, 1)))
+        except OSError:
+            pass
         _lib.rasterise_host(sol._case, spec.spheres, w)
         gl_r = w.reshape(3, sol.N3, sol.N2, sol.N1)[2, 2:-2, 2:-2, 2:-2]
         sol.upload_interior(u, p, np.ascontiguousarray(gl_r))
@@ -436,7 +441,8 @@ def stage_profile(b: Bench, H, peak, peak_src):
         gbs = b.sol.cells * sb[i] / (ms * 1e-3) / 1e9
         stages.append({"stage": i + 1, "launches": nl, "avg_ms": ms, "bytes_per_cell": sb[i], "achieved_gbs": gbs, "frac": gbs / peak})
     dom = max(stages, key=lambda s: s["avg_ms"] * s["launches"])
-    roofline = {"bound": "hbm", "kernel": f"merson_stage_tma<{dom['stage']}>", "achieved": dom["achieved_gbs"], "peak": peak,
+    gen = {0: "merson_stage", 1: "merson_stage_tma", 2: "merson_stage_v2"}.get(stp.get("kernel_generation", 1), "merson_stage")
+    roofline = {"bound": "hbm", "kernel": f"{gen}<{dom['stage']}>", "achieved": dom["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b.sol.cells * dom["bytes_per_cell"], "avg_launch_ms": dom["avg_ms"],
                 "per_stage": stages}

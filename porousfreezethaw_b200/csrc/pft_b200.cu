@@ -493,6 +493,7 @@ static int build_params(pft_solver *s)
 		kp.c = s->c;
 		kp.g = s->g;
 		kp.g.zc = cf.zc;
+		kp.smem_bytes = (unsigned)cf.smem;
 		StageArgs &a = kp.a;
 		memset(&a, 0, sizeof a);
 		a.ctl = s->ctl;
@@ -518,7 +519,7 @@ static int build_params(pft_solver *s)
 		if (s->use_tma) {
 			TmaParams &tp = s->tp[stage - 1];
 			tp.c = kp.c; tp.g = kp.g; tp.a = kp.a;
-			tp.bx = cf.bx; tp.by = cf.by; tp.as = cf.as; tp.tx = cf.TX; tp.ty = cf.TY;
+			tp.bx = cf.bx; tp.by = cf.by; tp.as = cf.as; tp.tx = cf.TX; tp.ty = cf.TY; tp.smem_bytes = (unsigned)cf.smem;
 			// array order of a stage: p-type arrays, u-type arrays, gl (pft_kernels_tma.cuh, stage_np); one tensor
 			// map per array with this stage's box
 			const int src[5][4] = {{A_X, -1, -1, -1}, {A_X, A_K1, -1, -1}, {A_A3, -1, -1, -1}, {A_X, A_K1, A_K3, -1}, {A_X, A_K1, A_K3, A_K4}};

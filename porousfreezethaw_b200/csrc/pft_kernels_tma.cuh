@@ -44,6 +44,7 @@ struct alignas(64) TmaParams {
 	int bx, by;                          // box extents: bx = TX+4 (TX even; the box starts at the even x = i0-2), by = TY+2
 	int as;                              // doubles per array buffer (bx*by rounded up to 16 = 128 B)
 	int tx, ty;                          // merson_stage_v2 (1-D thread block): threads per tile row / thread rows
+	unsigned smem_bytes;                 // dynamic shared memory of the launch
 };
 
 // number of p-type (and u-type) arrays stage S stages through shared memory
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(256, (STAGE == 5) ? 2 : 3) merson_stage_tma(co
 	}
 
 	halo_signal(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);
-	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
+	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite, smem_t, P.smem_bytes);
 }
 
 }  // namespace pft

@@ -288,7 +288,7 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 	if (it < nplanes) { plane(std::integral_constant<int, 1>(), it); it++; }
 
 	halo_signal(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);
-	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite);
+	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite, smem_t, P.smem_bytes);
 }
 
 }  // namespace pft
