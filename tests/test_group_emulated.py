@@ -112,3 +112,35 @@ def test_solver_module_abi_from_python(emu_lib, ngpus, mode):
         parity.assert_fields(case, xh, x, True, "through RK_MPI_SA_solve")
     finally:
         run.close()
+
+
+def test_host_right_hand_side_is_refused(emu_lib):
+    """A caller that hands the solver module a HOST right-hand side -- what the reference's DEM application does with
+    this ABI (apps/sphere-collider/spheres_friction_angular.c:573,606) -- is refused with the reference's error code
+    -2 (bad system); there is no CPU path.  Same for a DDLBF rearrangement hook and weighted chunks."""
+    import ctypes as C
+    import os
+    from porousfreezethaw_b200.dropin import DropInRun, META_F
+    rk_emu = os.path.join(os.path.dirname(emu_lib), "librk_b200_emu.so")
+    spec = cases.small_case(12, 10, 16, calc_mode=0)
+    case, orc, w = parity.make(spec)
+    run = DropInRun(spec, rk_path=rk_emu)
+    try:
+        RHS = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double))
+        host_rhs = RHS(lambda t, x, dx: None)
+        host_addr = C.cast(host_rhs, C.c_void_p).value
+        host_meta = META_F(lambda: host_addr)             # (kept alive in this frame: ctypes does not hold it for the struct)
+        run.system.meta_f = host_meta
+        xh = w.copy()
+        assert run.solve(xh, 1.0) == -2
+        assert np.array_equal(xh, w)                      # nothing was touched
+        run.system.meta_f = run._meta
+        run.system.DDLBF_Rearrange = 1
+        assert run.solve(xh, 1.0) == -2
+        run.system.DDLBF_Rearrange = None
+        run._mult[3] = 2.0
+        assert run.solve(xh, 1.0) == -2
+        run._mult[3] = 1.0
+        assert run.solve(xh, 1.0) == 0
+    finally:
+        run.close()
