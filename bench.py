@@ -447,7 +447,11 @@ def stage_profile(b: Bench, H, peak, peak_src):
                 "algorithmic_bytes_per_launch": b.sol.cells * dom["bytes_per_cell"], "avg_launch_ms": dom["avg_ms"],
                 "per_stage": stages}
     if b.N > 1:
-        roofline["note"] = "N > 1: a stage's event time includes waiting for the neighbouring slabs' boundary planes"
+        roofline["note"] = "N > 1: a stage's event time includes waiting for the neighbouring slabs' boundary planes (stage 5: for every slab's error maximum)"
+        mine = [round(stp["stage_ms"][i] / max(stp["stage_launches"][i], 1), 4) for i in range(5)]
+        allr = [None] * b.N
+        b.dist.all_gather_object(allr, (b.sol.n3, mine))
+        roofline["per_rank[planes, stage_ms x5]"] = allr
     tr = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes per launch from the committed ncu capture
     if os.path.exists(tr):
         try:

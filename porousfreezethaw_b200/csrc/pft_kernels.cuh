@@ -183,8 +183,10 @@ __device__ __forceinline__ double face_flux(const Consts &c, double pa, double p
 // so divide a harmless 1.0 instead and select the zero afterwards: every lane stays on the
 // correctly-rounded fast path, non-zero operands are untouched.
 // (Numerators below ~2^-960 -- the far tail of the phase field, 1e-290 ... 1e-323 -- still take the
-// subroutine.  An exact rescaling of those was built and verified bit for bit, and rejected: its
-// extra branches cost 3 % on every division, more than the tail costs; profiles/round1_tuning.md.)
+// subroutine.  Two exact remedies were built, verified bit for bit and rejected on measurement: a rescaling
+// in front of nvcc's division (round 1, -3 %) and a hand-written division with its own tiny/subnormal path
+// (round 2: 58.6 vs 59.0 Gcell-RHS/s early in the 400 case, 57.2 vs 57.5 after 1500 attempts when the tail has
+// spread over the domain; profiles/README.md).)
 __device__ __forceinline__ double div_pos(double a, double b)
 {
 	const bool z = (a == 0.0);

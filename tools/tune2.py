@@ -28,7 +28,7 @@ if os.environ.get("TUNE_ONLY"):
 rows = []
 for name, env in CONFIGS:
     e = dict(os.environ, **env)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", WORK, "--steps", "40", "--warmup", "10", "--repeats", "3",
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", WORK, "--steps", "40", "--warmup", os.environ.get("TUNE_WARMUP", "10"), "--repeats", "3",
                         "--also", "none", "--no-cpu-baseline", "--no-parity", "--no-dropin", "--profile-steps", "20"], capture_output=True, text=True, env=e, cwd=ROOT)
     line = [l for l in r.stdout.splitlines() if l.startswith("{")]
     if r.returncode or not line:
