@@ -458,8 +458,8 @@ def stage_profile(b: Bench, H, peak, peak_src):
             with open(tr) as f:
                 tj = json.load(f)
             key = f"{spec.name}:stage{dom['stage']}"
-            if key in tj:
-                roofline["traffic"] = tj[key]
+            if key in tj:      # captured on one GPU holding the whole grid; a slab moves its share
+                roofline["traffic"] = tj[key] * b.sol.cells / spec.cells
         except Exception:
             pass
     return roofline
