@@ -261,10 +261,41 @@ class Bench:
         self.args, self.spec, self.rank, self.N, self.local, self.dry, self.dist, self.torch = args, spec, rank, N, local, dry, dist, torch
         self.lib_path = lib_path
         self.SlabSolver = SlabSolver
+        self.planes = None                     # planes per slab; None = the reference's rule
+        self.balance = None
+        if N > 1 and not dry and not getattr(args, "no_balance", False):
+            self.calibrate()
         self.sol = self.new_solver()
 
+    def calibrate(self):
+        """Load balance (the multi-process counterpart of pft_group_balance): slabs differ in cost per plane (interior slabs
+        push two halo planes, the division's cost depends on the data) and every attempt ends with all slabs waiting for the
+        slowest.  A throw-away solver with per-stage device timing runs warm-up + 30 attempts from the initial state; the
+        planes are then dealt out in inverse proportion to the measured cost per plane (cases.balanced_planes)."""
+        from porousfreezethaw_b200.cases import balanced_planes, partition
+        os.environ["PFT_PROFILE_STAGES"] = "1"
+        sol = self.new_solver()
+        del os.environ["PFT_PROFILE_STAGES"]
+        try:
+            self.initial_state(sol)
+            sol.solve(self.spec.final_time, max_attempts=max(self.args.warmup, 3))
+            sol.reset_stats()
+            self.barrier()
+            sol.solve(self.spec.final_time, max_attempts=30)
+            st = sol.stats()
+        finally:
+            sol.close()
+        mine = sum(st["stage_ms"][i] / max(st["stage_launches"][i], 1) for i in range(4))      # stage 5 contains the wait for the others
+        allc = [None] * self.N
+        self.dist.all_gather_object(allc, float(mine))
+        planes0 = [partition(self.spec.n3, self.N, r)[0] for r in range(self.N)]
+        self.balance = {"cost_ms_stages_1_4": [round(c, 4) for c in allc], "planes_before": planes0}
+        if max(allc) > 1.03 * (sum(allc) / self.N) and min(allc) > 0:
+            self.planes = balanced_planes(planes0, allc)
+        self.balance["planes"] = self.planes or planes0
+
     def new_solver(self):
-        sol = self.SlabSolver(self.spec, rank=self.rank, nranks=self.N, device=self.local, lib_path=self.lib_path)
+        sol = self.SlabSolver(self.spec, rank=self.rank, nranks=self.N, device=self.local, lib_path=self.lib_path, planes=self.planes)
         if self.N > 1:
             torch, dist = self.torch, self.dist
             uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -510,6 +541,7 @@ def run_workload(args, name, rank, N, local, lib_path, dry, dist, torch, steps, 
         "device_ms_regions": [round(d, 4) for d in devs], "wall_ms_per_step": wall_ms / steps,
         "rhs_evals_per_attempt": rhs_per_region / steps,
         "rasterise_ms": {"ms": round(getattr(b, "rasterise_ms", 0.0), 3), "spheres": int(len(spec.spheres)), "cells_per_gpu": int(sol.cells)},
+        "slab_balance": b.balance,
         "roofline_step": {"achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                           "note": "algorithmic bytes of the stage kernels that did work in a timed region / its device time, per GPU (launch gaps included)"},
     }
@@ -531,6 +563,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: keep the reference's even slab partition (default: planes dealt out by measured cost)")
     ap.add_argument("--no-dropin", action="store_true", help="skip the end-to-end figure through RK_MPI_SA_solve (e2e_dropin)")
     ap.add_argument("--variant", default="strict", choices=["strict", "fast"],
                     help="strict = IEEE association, bit-exact (default); fast = FMA contraction allowed (fields within 1e-10, no step-sequence parity)")
@@ -710,6 +743,7 @@ def main():
             "roofline_step": frag["roofline_step"],
             "e2e_dropin": e2e_dropin,
             "rasterise_ms": frag["rasterise_ms"],
+            "slab_balance": frag["slab_balance"],
             "parity": parity,
             "also": also,
         }

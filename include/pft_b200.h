@@ -83,6 +83,10 @@ typedef struct {
 	int calc_mode;           /* 0 GradP, 1 SigmaP1-P, 2 temperature model, 10/11 = 0/1 without heat equation */
 	double L1, L2, L3;       /* domain size */
 	double param[PFT_NPARAM];/* model_parameters[], model.c:44-59 order */
+	int max_n3;              /* deepest slab of the run; 0 = the reference's partition rule (total_n3/nranks, remainder to
+	                            the lowest ranks).  Results do not depend on how the planes are dealt out, so a caller may
+	                            give slower slabs fewer planes (pft_group_* does that by itself); every rank passes the
+	                            same max_n3 >= its n3. */
 } pft_case;
 
 /* service callback: RK_MPI_S_SOLUTION.Service_Callback (RK_MPI_SAsolver.h:266-279) */
@@ -170,6 +174,15 @@ int pft_comm_init(pft_solver *s, const void *id128);
  * The slabs reach each other through peer access (NVLink), no NCCL.  x_padded is the one padded host array of
  * the whole block; the service callback is invoked by slab 0's worker only. */
 int pft_group_create(const pft_case *whole, int ngpus, const int *devices, unsigned flags, pft_group **out);
+/* the same with a given number of planes per slab (sum == whole->n3, every slab >= 2 planes); planes == NULL: the rule above */
+int pft_group_create_planes(const pft_case *whole, int ngpus, const int *devices, const int *planes, unsigned flags, pft_group **out);
+/* Load balance: slabs differ in cost per plane (interior slabs push two halo planes, the division's cost depends on the data),
+ * and every attempt ends with all slabs waiting for the slowest.  pft_group_balance runs `attempts` attempts with per-stage
+ * device timing, and if the slowest slab is more than 3 % above the mean it deals the planes out again in inverse proportion
+ * to the measured cost per plane (state carried over through a host copy).  Returns 1 if the partition changed, 0 if not.
+ * pft_group_solve calls it once by itself after the first 30 attempts unless PFT_BALANCE=0.  The planes in use: */
+int pft_group_balance(pft_group *g, pft_system *sys, double final_time, int attempts);
+int pft_group_planes(const pft_group *g, int *planes);
 int pft_group_destroy(pft_group *g);
 int pft_group_size(const pft_group *g);
 pft_solver *pft_group_member(pft_group *g, int r);

@@ -21,7 +21,7 @@ class PftCase(C.Structure):
     _fields_ = [("n1", C.c_int), ("n2", C.c_int), ("n3", C.c_int), ("total_n3", C.c_int),
                 ("first_row", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("calc_mode", C.c_int),
                 ("L1", C.c_double), ("L2", C.c_double), ("L3", C.c_double),
-                ("param", C.c_double * NPARAM)]
+                ("param", C.c_double * NPARAM), ("max_n3", C.c_int)]
 
 
 SERVICE_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.c_double, C.c_double, C.c_long, C.c_long, C.c_void_p)
@@ -53,7 +53,7 @@ EXPORTS = [
     "pft_ice_fraction", "pft_comm_unique_id", "pft_comm_init", "pft_get_stats", "pft_reset_stats",
     "pft_debug_fetch", "pft_debug_pow", "pft_upload_fields", "pft_download_fields", "pft_host_register", "pft_host_unregister",
     "pft_group_create", "pft_group_destroy", "pft_group_size", "pft_group_member", "pft_group_upload", "pft_group_download",
-    "pft_group_solve",
+    "pft_group_solve", "pft_group_create_planes", "pft_group_balance", "pft_group_planes",
 ]
 
 _cache: dict[str, C.CDLL] = {}
@@ -101,6 +101,9 @@ def load(path: str | None = None) -> C.CDLL:
     lib.pft_group_upload.argtypes = [vp, _dp, C.c_uint]
     lib.pft_group_download.argtypes = [vp, _dp, C.c_uint]
     lib.pft_group_solve.argtypes = [vp, C.POINTER(PftSystem), C.c_double]
+    lib.pft_group_create_planes.argtypes = [C.POINTER(PftCase), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_uint, C.POINTER(vp)]
+    lib.pft_group_balance.argtypes = [vp, C.POINTER(PftSystem), C.c_double, C.c_int]
+    lib.pft_group_planes.argtypes = [vp, C.POINTER(C.c_int)]
     for name in EXPORTS:
         getattr(lib, name)
     _cache[path] = lib

@@ -204,3 +204,26 @@ def partition(total_n3: int, nranks: int, rank: int):
     if rank < r:
         return q + 1, rank * q + rank
     return q, rank * q + r
+
+
+def balanced_planes(planes, cost):
+    """Planes per slab in inverse proportion to the measured cost per plane (`cost[r]` = device time per attempt of slab r
+    with `planes[r]` planes), every slab keeps >= 2 planes, the sum is exact -- the rule of pft_group_balance
+    (csrc/pft_b200.cu: balanced_planes), for callers that own one slab per process."""
+    n, total = len(planes), int(sum(planes))
+    w = [planes[r] / cost[r] for r in range(n)]
+    ws = sum(w)
+    out = [max(2, int(math.floor(total * w[r] / ws))) for r in range(n)]
+    given = sum(out)
+    while given != total:
+        best, bestv = -1, 0.0
+        for r in range(n):
+            frac = total * w[r] / ws - out[r]
+            v = frac if given < total else -frac
+            if (given < total or out[r] > 2) and (best < 0 or v > bestv):
+                best, bestv = r, v
+        if best < 0:
+            break
+        out[best] += 1 if given < total else -1
+        given += 1 if given < total else -1
+    return out

@@ -29,6 +29,7 @@ static void pft_plugin_fill_case(pft_case *c)
 	c->rank = MPIrank; c->nranks = MPIprocs;
 	c->calc_mode = calc_mode;
 	c->L1 = L1; c->L2 = L2; c->L3 = L3;
+	c->max_n3 = 0;               /* the application's own slab partition (intertrack.c:1780-1787) */
 	for (q = 0; q < PARAM_COUNT && q < PFT_NPARAM; q++) c->param[q] = param[q];
 }
 

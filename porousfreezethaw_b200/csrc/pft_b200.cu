@@ -227,6 +227,9 @@ struct pft_solver {
 struct pft_group {
 	int n;
 	pft_case whole;
+	unsigned flags;
+	std::vector<int> devices, planes;
+	bool balance_tried;       // pft_group_solve rebalances once by itself
 	std::vector<pft_solver *> member;
 	// service callback agreement: slab 0's worker calls the user's callback, the others take its verdict
 	pft_service_fn user_service;
@@ -659,12 +662,13 @@ static int setup_p2p(pft_solver *s)
 {
 	const int R = s->cs.nranks, r = s->cs.rank;
 	if (R > PFT_MAX_RANKS) return fail(PFT_EINVAL, "peer path supports at most %d ranks", PFT_MAX_RANKS);
-	struct Export { cudaIpcMemHandle_t h; int n3; int ok; unsigned long long bytes; };
+	struct Export { cudaIpcMemHandle_t h; int n3, first_row; int ok; unsigned long long bytes; };
 	Export mine;
 	memset(&mine, 0, sizeof mine);
 	mine.ok = (cudaIpcGetMemHandle(&mine.h, s->slab) == cudaSuccess);
 	if (!mine.ok) cudaGetLastError();
 	mine.n3 = s->cs.n3;
+	mine.first_row = s->cs.first_row;
 	mine.bytes = s->slab_bytes;
 	Export *d = nullptr;
 	std::vector<Export> all(R);
@@ -675,11 +679,15 @@ static int setup_p2p(pft_solver *s)
 	CU(cudaStreamSynchronize(s->stream));
 	cudaFree(d);
 	bool ok = true;
+	int row = all[0].first_row;
 	for (int q = 0; q < R; q++) {
-		ok = ok && all[q].ok && all[q].bytes == s->slab_bytes;
-		if (all[q].n3 != slab_n3(s->cs.total_n3, R, q)) return fail(PFT_EINVAL, "rank %d holds %d planes, expected %d", q, all[q].n3, slab_n3(s->cs.total_n3, R, q));
+		ok = ok && all[q].ok;
+		if (all[q].bytes != s->slab_bytes) return fail(PFT_EINVAL, "rank %d sized its slab differently (%llu vs %zu bytes): every rank must pass the same max_n3", q, all[q].bytes, s->slab_bytes);
+		if (all[q].first_row != row || all[q].n3 < 1) return fail(PFT_EINVAL, "the slabs do not tile the grid: rank %d starts at plane %d, expected %d", q, all[q].first_row, row);
+		row += all[q].n3;
 		s->peer_n3[q] = all[q].n3;
 	}
+	if (row - all[0].first_row != s->cs.total_n3) return fail(PFT_EINVAL, "the slabs hold %d planes, the grid has %d", row - all[0].first_row, s->cs.total_n3);
 	if (ok) {
 		for (int q = 0; q < R && ok; q++) {
 			if (q == r) { s->peer_base[q] = s->slab; continue; }
@@ -746,6 +754,7 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	*out = nullptr;
 	if (cs->n1 < 1 || cs->n2 < 1 || cs->n3 < 1 || cs->total_n3 < cs->n3) return fail(PFT_EINVAL, "bad grid %dx%dx%d (total_n3 %d)", cs->n1, cs->n2, cs->n3, cs->total_n3);
 	if (cs->nranks < 1 || cs->rank < 0 || cs->rank >= cs->nranks) return fail(PFT_EINVAL, "bad rank %d of %d", cs->rank, cs->nranks);
+	if (cs->max_n3 != 0 && cs->max_n3 < cs->n3) return fail(PFT_EINVAL, "max_n3 %d is smaller than this slab (%d planes)", cs->max_n3, cs->n3);
 	switch (cs->calc_mode) { case 0: case 1: case 2: case 10: case 11: break; default: return fail(PFT_EINVAL, "invalid calc_mode %d", cs->calc_mode); }
 	if (cs->param[P_u_noise_amp] != 0.0)
 		return fail(PFT_EINVAL, "u_noise_amp != 0 is not supported (the reference seeds its noise field from time(), intertrack.c:1278)");
@@ -781,7 +790,8 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	g.rear = (cs->rank == cs->nranks - 1);
 	// every rank sizes its arrays for the deepest slab so that array offsets inside the slab are
 	// the same on all ranks (peers address each other's arrays by offset)
-	s->field = g.plane * ((cs->total_n3 + cs->nranks - 1) / cs->nranks + 2);
+	s->field = g.plane * ((cs->max_n3 > 0 ? cs->max_n3 : (cs->total_n3 + cs->nranks - 1) / cs->nranks) + 2);
+	if (s->field < g.plane * (cs->n3 + 2)) { delete s; return fail(PFT_EINVAL, "slab of %d planes exceeds the run's deepest slab; pass max_n3", cs->n3); }
 	s->N1 = cs->n1 + 2 * PFT_BT; s->N2 = cs->n2 + 2 * PFT_BT; s->N3 = cs->n3 + 2 * PFT_BT;
 	s->padded = (long long)PFT_NVAR * s->N1 * s->N2 * s->N3;
 
@@ -1464,42 +1474,41 @@ device_error:
 extern "C" int pft_group_size(const pft_group *g) { return g ? g->n : 0; }
 extern "C" pft_solver *pft_group_member(pft_group *g, int r) { return (g && r >= 0 && r < g->n) ? g->member[r] : nullptr; }
 
+static void group_free_members(pft_group *g)
+{
+	for (pft_solver *m : g->member) pft_destroy(m);
+	g->member.clear();
+}
+
 extern "C" int pft_group_destroy(pft_group *g)
 {
 	if (!g) return 0;
-	for (pft_solver *m : g->member) pft_destroy(m);
+	group_free_members(g);
 	delete g;
 	return 0;
 }
 
-extern "C" int pft_group_create(const pft_case *whole, int ngpus, const int *devices, unsigned flags, pft_group **out)
+// create the member solvers for g->planes and wire them to each other
+static int group_build_members(pft_group *g)
 {
-	if (!whole || !out || ngpus < 1) return fail(PFT_EINVAL, "bad argument");
-	*out = nullptr;
-	if (whole->nranks != 1 || whole->rank != 0) return fail(PFT_EINVAL, "pft_group_create takes the whole block of a single-rank run");
-	if (ngpus > PFT_MAX_RANKS) return fail(PFT_EINVAL, "at most %d GPUs per group", PFT_MAX_RANKS);
-	if (whole->n3 / ngpus < 1) return fail(PFT_EINVAL, "%d planes cannot be cut into %d slabs", whole->n3, ngpus);
-	pft_group *g = new (std::nothrow) pft_group();
-	if (!g) return fail(PFT_ENOMEM, "out of host memory");
-	g->n = ngpus; g->whole = *whole;
-	g->user_service = nullptr; g->user_ctx = nullptr;
-	g->cb_seq.store(-1); g->cb_val.store(0);
-	int first = whole->first_row;
+	const pft_case *whole = &g->whole;
+	const int ngpus = g->n;
+	int first = whole->first_row, deepest = 0;
+	for (int r = 0; r < ngpus; r++) deepest = std::max(deepest, g->planes[r]);
 	for (int r = 0; r < ngpus; r++) {
 		pft_case c = *whole;
 		c.rank = r; c.nranks = ngpus;
-		c.n3 = slab_n3(whole->n3, ngpus, r);          // intertrack.c:1780-1787
+		c.n3 = g->planes[r];
 		c.first_row = first;
+		c.max_n3 = deepest;
 		first += c.n3;
 		// (total_n3 stays the whole grid's: the z grid spacing comes from it, equation.c:607)
 		pft_solver *m = nullptr;
-		int rc = pft_create(&c, devices ? devices[r] : r, flags, &m);
-		if (rc) { pft_group_destroy(g); return rc; }
+		int rc = pft_create(&c, g->devices[r], g->flags, &m);
+		if (rc) { group_free_members(g); return rc; }
 		m->group = g;
 		g->member.push_back(m);
 	}
-	// the slab-local geometry above deviates from a true ngpus-rank run in one respect only: the group owns the
-	// physical z boundaries of `whole`, which may itself be a slab of a larger multi-process run -- not supported yet
 	if (ngpus > 1) {
 #ifndef PFT_CUDA_EMU
 		for (int r = 0; r < ngpus; r++)
@@ -1507,10 +1516,10 @@ extern "C" int pft_group_create(const pft_case *whole, int ngpus, const int *dev
 				if (q == r || g->member[q]->device == g->member[r]->device) continue;
 				int can = 0;
 				cudaDeviceCanAccessPeer(&can, g->member[r]->device, g->member[q]->device);
-				if (!can) { pft_group_destroy(g); return fail(PFT_ENODEVICE, "device %d cannot access device %d: the in-process group needs peer access (NVLink)", g->member[r]->device, g->member[q]->device); }
+				if (!can) { int a_ = g->member[r]->device, b_ = g->member[q]->device; group_free_members(g); return fail(PFT_ENODEVICE, "device %d cannot access device %d: the in-process group needs peer access (NVLink)", a_, b_); }
 				cudaSetDevice(g->member[r]->device);
 				cudaError_t e = cudaDeviceEnablePeerAccess(g->member[q]->device, 0);
-				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { pft_group_destroy(g); return fail(PFT_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); }
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { group_free_members(g); return fail(PFT_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); }
 				cudaGetLastError();
 			}
 #endif
@@ -1521,8 +1530,46 @@ extern "C" int pft_group_create(const pft_case *whole, int ngpus, const int *dev
 			m->params_ok = false;
 		}
 	}
+	return 0;
+}
+
+extern "C" int pft_group_create_planes(const pft_case *whole, int ngpus, const int *devices, const int *planes, unsigned flags, pft_group **out)
+{
+	if (!whole || !out || ngpus < 1) return fail(PFT_EINVAL, "bad argument");
+	*out = nullptr;
+	if (whole->nranks != 1 || whole->rank != 0) return fail(PFT_EINVAL, "pft_group_create takes the whole block of a single-rank run");
+	if (ngpus > PFT_MAX_RANKS) return fail(PFT_EINVAL, "at most %d GPUs per group", PFT_MAX_RANKS);
+	if (whole->n3 / ngpus < 1) return fail(PFT_EINVAL, "%d planes cannot be cut into %d slabs", whole->n3, ngpus);
+	pft_group *g = new (std::nothrow) pft_group();
+	if (!g) return fail(PFT_ENOMEM, "out of host memory");
+	g->n = ngpus; g->whole = *whole; g->flags = flags;
+	g->user_service = nullptr; g->user_ctx = nullptr;
+	g->cb_seq.store(-1); g->cb_val.store(0);
+	g->balance_tried = (ngpus == 1) || env_int("PFT_BALANCE", 1) == 0 || planes != nullptr;
+	int sum = 0;
+	for (int r = 0; r < ngpus; r++) {
+		g->devices.push_back(devices ? devices[r] : r);
+		g->planes.push_back(planes ? planes[r] : slab_n3(whole->n3, ngpus, r));          // intertrack.c:1780-1787
+		sum += g->planes[r];
+		if (g->planes[r] < 2 && ngpus > 1) { delete g; return fail(PFT_EINVAL, "slab %d would hold fewer than 2 planes", r); }
+	}
+	if (sum != whole->n3) { delete g; return fail(PFT_EINVAL, "the slabs hold %d planes, the block has %d", sum, whole->n3); }
+	int rc = group_build_members(g);
+	if (rc) { delete g; return rc; }
 	*out = g;
 	return 0;
+}
+
+extern "C" int pft_group_create(const pft_case *whole, int ngpus, const int *devices, unsigned flags, pft_group **out)
+{
+	return pft_group_create_planes(whole, ngpus, devices, nullptr, flags, out);
+}
+
+extern "C" int pft_group_planes(const pft_group *g, int *planes)
+{
+	if (!g || !planes) return fail(PFT_EINVAL, "null argument");
+	for (int r = 0; r < g->n; r++) planes[r] = g->planes[r];
+	return g->n;
 }
 
 // the slabs of ONE padded host array: slab r's padded plane 0 is the whole block's padded plane (first_row_r - first_row_0)
@@ -1586,9 +1633,9 @@ static int group_service_follower(double, double, double, long, long steps_total
 	return g->cb_val.load(std::memory_order_relaxed);
 }
 
-extern "C" int pft_group_solve(pft_group *g, pft_system *sys, double final_time)
+// one worker thread per slab, each the ordinary pft_solve host loop on its own device
+static int group_run(pft_group *g, pft_system *sys, double final_time)
 {
-	if (!g || !sys) { fail(PFT_EINVAL, "null argument"); return PFT_SOLVE_BADSYSTEM; }
 	if (g->n == 1) return pft_solve(g->member[0], sys, final_time);
 	std::vector<pft_system> ss(g->n, *sys);
 	std::vector<int> rcs(g->n, 0);
@@ -1616,6 +1663,119 @@ extern "C" int pft_group_solve(pft_group *g, pft_system *sys, double final_time)
 	*sys = ss[0];
 	sys->service = keep_fn; sys->service_ctx = keep_ctx;
 	return rcs[0];
+}
+
+// planes in inverse proportion to the measured cost per plane (every slab keeps >= 2 planes, the sum is exact)
+static std::vector<int> balanced_planes(const std::vector<int> &planes, const std::vector<double> &cost)
+{
+	const int n = (int)planes.size();
+	int total = 0;
+	double wsum = 0.0;
+	std::vector<double> w(n);
+	for (int r = 0; r < n; r++) { total += planes[r]; w[r] = planes[r] / cost[r]; wsum += w[r]; }
+	std::vector<int> out(n);
+	int given = 0;
+	for (int r = 0; r < n; r++) { out[r] = std::max(2, (int)floor(total * w[r] / wsum)); given += out[r]; }
+	// deal the remainder (or take back an excess) one plane at a time, largest fractional part first
+	while (given != total) {
+		int best = -1;
+		double bestv = 0.0;
+		for (int r = 0; r < n; r++) {
+			const double frac = total * w[r] / wsum - out[r];
+			const double v = (given < total) ? frac : -frac;
+			if ((given < total || out[r] > 2) && (best < 0 || v > bestv)) { best = r; bestv = v; }
+		}
+		if (best < 0) break;
+		out[best] += (given < total) ? 1 : -1;
+		given += (given < total) ? 1 : -1;
+	}
+	return out;
+}
+
+// *solve_rc: what the calibration attempts did to the integration (PFT_SOLVE_*; the caller's budget is accounted for)
+static int group_balance(pft_group *g, pft_system *sys, double final_time, int attempts, int *solve_rc)
+{
+	*solve_rc = PFT_SOLVE_BUDGET;
+	g->balance_tried = true;
+	if (g->n < 2 || attempts < 1) return 0;
+	// ---- `attempts` attempts with per-stage device timing (events around every launch, one attempt in flight)
+	std::vector<pft_stats> before(g->n);
+	for (int r = 0; r < g->n; r++) { pft_solver *m = g->member[r]; before[r] = m->st; m->profile = true; m->pdl = false; }
+	const long keep_budget = sys->max_attempts;
+	sys->max_attempts = (keep_budget > 0) ? std::min<long>(keep_budget, attempts) : attempts;
+	const long t0 = sys->steps_total;
+	const int rc = group_run(g, sys, final_time);
+	const long used = sys->steps_total - t0;
+	sys->max_attempts = keep_budget;
+	for (int r = 0; r < g->n; r++) { pft_solver *m = g->member[r]; m->profile = env_int("PFT_PROFILE_STAGES", 0) != 0; m->pdl = !m->profile && env_int("PFT_NO_PDL", 0) == 0; }
+	*solve_rc = rc;
+	if (rc == PFT_SOLVE_BUDGET && !(keep_budget > 0 && used >= keep_budget)) *solve_rc = -1000;      // only the calibration's own budget ran out: go on
+	if (rc < 0) return rc == PFT_SOLVE_NAN ? 0 : rc;
+	// stages 1-4 (stage 5's time contains the wait for every slab's error maximum): device ms per attempt
+	std::vector<double> cost(g->n, 0.0);
+	double mean = 0.0, worst = 0.0;
+	for (int r = 0; r < g->n; r++) {
+		const pft_stats &a = g->member[r]->st, &b0 = before[r];
+		for (int st = 0; st < 4; st++) {
+			const long nl = a.stage_launches[st] - b0.stage_launches[st];
+			if (nl > 0) cost[r] += (a.stage_ms[st] - b0.stage_ms[st]) / nl;
+		}
+	}
+	if (const char *forced = getenv("PFT_BALANCE_COSTS")) {      // test hook: "c0,c1,..." instead of the measured costs
+		for (int r = 0; r < g->n && forced && *forced; r++) {
+			cost[r] = atof(forced);
+			forced = strchr(forced, ',');
+			if (forced) forced++;
+		}
+	}
+	for (int r = 0; r < g->n; r++) {
+		if (!(cost[r] > 0.0)) return 0;
+		mean += cost[r] / g->n;
+		worst = std::max(worst, cost[r]);
+	}
+	if (worst <= 1.03 * mean) return 0;
+	const std::vector<int> planes = balanced_planes(g->planes, cost);
+	if (planes == g->planes) return 0;
+	// ---- deal the planes out again: the state travels through one padded host array of the whole block
+	const pft_case &w = g->whole;
+	const size_t nd = (size_t)PFT_NVAR * (w.n1 + 2 * PFT_BT) * (w.n2 + 2 * PFT_BT) * (size_t)(w.n3 + 2 * PFT_BT);
+	double *x = (double *)calloc(nd, sizeof(double));
+	if (!x) return fail(PFT_ENOMEM, "out of host memory for the rebalancing copy (%zu doubles)", nd);
+	int rc2 = pft_group_download(g, x, PFT_FIELD_ALL);
+	if (!rc2) {
+		group_free_members(g);
+		g->planes = planes;
+		rc2 = group_build_members(g);
+	}
+	if (!rc2) rc2 = pft_group_upload(g, x, PFT_FIELD_ALL);
+	free(x);
+	if (rc2) return rc2;
+	return 1;
+}
+
+extern "C" int pft_group_balance(pft_group *g, pft_system *sys, double final_time, int attempts)
+{
+	if (!g || !sys) return fail(PFT_EINVAL, "null argument");
+	int solve_rc;
+	return group_balance(g, sys, final_time, attempts, &solve_rc);
+}
+
+extern "C" int pft_group_solve(pft_group *g, pft_system *sys, double final_time)
+{
+	if (!g || !sys) { fail(PFT_EINVAL, "null argument"); return PFT_SOLVE_BADSYSTEM; }
+	if (!g->balance_tried) {
+		// the first 30 attempts of the first solve call double as the calibration run (through the ordinary loop)
+		const long t0 = sys->steps_total, budget = sys->max_attempts;
+		int solve_rc;
+		const int rb = group_balance(g, sys, final_time, 30, &solve_rc);
+		if (rb < 0) return rb;
+		if (solve_rc != -1000) return solve_rc;              // finished, interrupted, NaN abort or the caller's own budget
+		if (budget > 0) sys->max_attempts = budget - (sys->steps_total - t0);
+		const int rc = group_run(g, sys, final_time);
+		sys->max_attempts = budget;
+		return rc;
+	}
+	return group_run(g, sys, final_time);
 }
 
 extern "C" int pft_get_stats(pft_solver *s, pft_stats *out)

@@ -59,14 +59,22 @@ class SlabSolver:
     reference's (solution array, RK_MPI_S_SOLUTION) pair."""
 
     def __init__(self, spec: CaseSpec, rank: int = 0, nranks: int = 1, device: int = 0, flags: int = 0,
-                 lib_path: str | None = None):
+                 lib_path: str | None = None, planes=None):
+        """planes: planes per slab for all ranks (sum == spec.n3); None = the reference's rule (intertrack.c:1780-1787).
+        Results do not depend on it; slower slabs can be given fewer planes (cases.balanced_planes)."""
         self.lib = _lib.load(lib_path)
         self.spec = spec
         self.rank, self.nranks = rank, nranks
-        self.n3, self.first_row = partition(spec.n3, nranks, rank)
+        if planes is None:
+            self.n3, self.first_row = partition(spec.n3, nranks, rank)
+            deepest = 0
+        else:
+            assert len(planes) == nranks and sum(planes) == spec.n3 and min(planes) >= 1
+            self.n3, self.first_row, deepest = int(planes[rank]), int(sum(planes[:rank])), int(max(planes))
         self.n1, self.n2 = spec.n1, spec.n2
         cc = _lib.PftCase(spec.n1, spec.n2, self.n3, spec.n3, self.first_row, rank, nranks, spec.calc_mode,
                           spec.L1, spec.L2, spec.L3)
+        cc.max_n3 = deepest
         par = spec.param_array()
         for i in range(_lib.NPARAM):
             cc.param[i] = float(par[i])
@@ -210,7 +218,9 @@ class GroupSolver:
     """The whole block of a case on several GPUs of ONE host process (pft_group_*): what the reference does
     with M MPI ranks inside one application run.  Host data is the one padded array of the whole block."""
 
-    def __init__(self, spec: CaseSpec, ngpus: int, devices=None, flags: int = 0, lib_path: str | None = None):
+    def __init__(self, spec: CaseSpec, ngpus: int, devices=None, flags: int = 0, lib_path: str | None = None, planes=None):
+        """planes: planes per slab (sum == spec.n3); None = the reference's rule, rebalanced once by the library
+        after the first 30 attempts (pft_group_balance) unless PFT_BALANCE=0"""
         self.lib = _lib.load(lib_path)
         self.spec = spec
         self.ngpus = ngpus
@@ -221,7 +231,8 @@ class GroupSolver:
             cc.param[i] = float(par[i])
         dev = (C.c_int * ngpus)(*(devices if devices is not None else range(ngpus)))
         h = C.c_void_p()
-        rc = self.lib.pft_group_create(C.byref(cc), ngpus, dev, flags, C.byref(h))
+        pl = None if planes is None else (C.c_int * ngpus)(*[int(v) for v in planes])
+        rc = self.lib.pft_group_create_planes(C.byref(cc), ngpus, dev, pl, flags, C.byref(h))
         if rc:
             raise PftError(f"pft_group_create failed ({rc}): {self.lib.pft_last_error().decode()}")
         self._h = h
@@ -265,6 +276,18 @@ class GroupSolver:
             raise PftError(f"pft_group_solve failed ({rc}): {self.lib.pft_last_error().decode()}")
         s = self.sys
         return SolveResult(rc, s.t, s.h, s.steps, s.steps_total, s.rhs_evals, s.last_nan)
+
+    def planes(self):
+        out = (C.c_int * self.ngpus)()
+        self.lib.pft_group_planes(self._h, out)
+        return list(out)
+
+    def balance(self, final_time: float, attempts: int = 30) -> int:
+        """pft_group_balance: calibrate over `attempts` attempts and deal the planes out again; 1 if the partition changed"""
+        rc = self.lib.pft_group_balance(self._h, C.byref(self.sys), final_time, attempts)
+        if rc < 0:
+            raise PftError(f"pft_group_balance failed ({rc}): {self.lib.pft_last_error().decode()}")
+        return rc
 
     def member_stats(self, r: int) -> dict:
         st = _lib.PftStats()

@@ -51,7 +51,8 @@ def main():
     nccl.emu_nccl_set_hooks(*hooks)
 
     spec = cases.small_case(12, 10, 18, calc_mode=mode)
-    sol = SlabSolver(spec, rank=rank, nranks=world, lib_path=os.path.join(EMU, "libpft_b200_emu.so"))
+    planes = [int(v) for v in os.environ["PFT_TEST_PLANES"].split(",")] if os.environ.get("PFT_TEST_PLANES") else None
+    sol = SlabSolver(spec, rank=rank, nranks=world, lib_path=os.path.join(EMU, "libpft_b200_emu.so"), planes=planes)
     uid = [sol.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, 0)
     sol.comm_init(uid[0])

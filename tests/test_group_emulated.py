@@ -144,3 +144,68 @@ def test_host_right_hand_side_is_refused(emu_lib):
         assert run.solve(xh, 1.0) == 0
     finally:
         run.close()
+
+
+@pytest.mark.parametrize("planes", [[3, 9, 7], [10, 2, 2, 5], [2, 17]])
+def test_group_uneven_partition_is_bit_exact(emu_lib, planes):
+    """results do not depend on how the planes are dealt out to the slabs"""
+    spec = cases.small_case(12, 10, sum(planes), calc_mode=0)
+    case, orc, w = parity.make(spec)
+    x = w.copy()
+    s = orc.new_system(t=0.0, h=spec.tau, h_min=spec.tau_min, delta=spec.delta)
+    work = np.zeros(5 * x.size)
+    g = GroupSolver(spec, len(planes), lib_path=emu_lib, planes=planes)
+    try:
+        assert g.planes() == planes
+        g.upload(w.copy())
+        for T in (4.0, 9.0):
+            assert orc.solve(s, x, T, work) == 0
+            r = g.solve(T)
+            assert (r.code, r.t, r.h, r.steps, r.steps_total) == (0, s.t, s.h, s.steps, s.steps_total)
+        got = w.copy()
+        g.download(got)
+        parity.assert_fields(case, got, x, True, "uneven slabs")
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("service", [False, True])
+def test_group_rebalances_itself(emu_lib, monkeypatch, service):
+    """pft_group_solve calibrates over its first 30 attempts and deals the planes out again (here with given costs:
+    the emulation has no device clock); the integration goes on from the migrated state, bit for bit, also across
+    a caller's attempt budget and with a callback"""
+    monkeypatch.setenv("PFT_BALANCE_COSTS", "1.0,1.6,1.2")
+    spec = cases.small_case(12, 10, 21, calc_mode=1)
+    case, orc, w = parity.make(spec)
+    x = w.copy()
+    rec_o, rec_g = [], []
+    s = orc.new_system(t=0.0, h=spec.tau, h_min=spec.tau_min, delta=spec.delta,
+                       service=(lambda ft, t, h, st, tot, ctx: rec_o.append((t, h)) or 0) if service else None)
+    work = np.zeros(5 * x.size)
+    g = GroupSolver(spec, 3, lib_path=emu_lib)
+    try:
+        assert g.planes() == [7, 7, 7]
+        g.upload(w.copy())
+        if service:
+            g.set_service(lambda ft, t, h, st, tot: rec_g.append((t, h)) or 0)
+        for T, budget in ((400.0, 12), (400.0, 25), (400.0, 0)):
+            s.max_attempts = budget
+            ro = orc.solve(s, x, T, work)
+            r = g.solve(T, max_attempts=budget)
+            assert r.code == ro
+            assert (r.t, r.h, r.steps, r.steps_total) == (s.t, s.h, s.steps, s.steps_total)
+        assert s.steps_total > 40
+        assert g.planes() != [7, 7, 7] and sum(g.planes()) == 21 and g.planes()[1] < 7
+        assert rec_g == rec_o
+        got = w.copy()
+        g.download(got)
+        parity.assert_fields(case, got, x, True, "after rebalancing")
+    finally:
+        g.close()
+
+
+def test_balanced_planes_rule():
+    assert cases.balanced_planes([100, 100, 100, 100], [317, 357, 332, 312]) == [104, 92, 99, 105]
+    assert sum(cases.balanced_planes([50] * 8, [1, 1.2, 1.1, 1.3, 1.0, 1.05, 1.15, 0.9])) == 400
+    assert cases.balanced_planes([7, 7, 7], [1.0, 1.0, 1.0]) == [7, 7, 7]
+    assert min(cases.balanced_planes([3, 3, 3], [1.0, 50.0, 1.0])) == 2

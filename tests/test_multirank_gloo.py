@@ -24,8 +24,9 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,mode", [(2, 0), (3, 1), (2, 11)])
-def test_slab_decomposition_is_bit_exact(world, mode, emu_lib, tmp_path):
+@pytest.mark.parametrize("world,mode,planes", [(2, 0, None), (3, 1, None), (2, 11, None), (3, 0, "4,9,5")])
+def test_slab_decomposition_is_bit_exact(world, mode, planes, emu_lib, tmp_path):
+    """one process per slab, NCCL transport (gloo standing in); planes: an uneven partition (pft_case.max_n3)"""
     T = 6.0
     spec = cases.small_case(12, 10, 18, calc_mode=mode)
     case, orc, w = parity.make(spec)
@@ -40,7 +41,8 @@ def test_slab_decomposition_is_bit_exact(world, mode, emu_lib, tmp_path):
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                   PFT_NCCL_LIB=os.path.join(ROOT, "tests", "cuda_emu", "libnccl_emu.so"), OMP_NUM_THREADS="1")
+                   PFT_NCCL_LIB=os.path.join(ROOT, "tests", "cuda_emu", "libnccl_emu.so"), OMP_NUM_THREADS="1",
+                   PFT_TEST_PLANES=planes or "")
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_gloo_worker.py"), str(mode), str(T), str(tmp_path)],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     outs = [pr.communicate(timeout=600)[0].decode() for pr in procs]
