@@ -221,6 +221,10 @@ struct pft_solver {
 	bool params_ok;
 	KParams kp[5];
 	TmaParams tp[5];
+	// stage-to-stage data flow (pft_kernels.cuh, dep_wait): completion words of the CTAs of stages 1-4
+	bool dataflow;
+	unsigned long long *done[4];
+	unsigned long long lseq;                   // attempts enqueued so far (host count; the flags carry it)
 };
 
 // one host process, several GPUs: slab r of the block lives on devices[r]
@@ -513,6 +517,9 @@ static int build_params(pft_solver *s)
 		else a.pr.nzc = cf.nzc;
 		a.pr.rank = s->cs.rank;
 		a.pr.nranks = s->p2p ? s->cs.nranks : 1;       // the in-kernel error-max exchange exists on the peer path only
+		a.dataflow = s->dataflow ? 1 : 0;
+		a.done_mine = (s->dataflow && stage <= 4) ? s->done[stage - 1] : nullptr;
+		a.done_prev = (s->dataflow && stage >= 2) ? s->done[stage - 2] : nullptr;
 		if (stage == 5) {
 			a.slot = s->slot_dev;
 			a.tab = s->tab_dev;
@@ -554,6 +561,8 @@ static int launch_stage(pft_solver *s, int stage, const double *standalone_dir =
 		cudaEventRecord(tm.a, s->stream);
 	}
 	cudaError_t e;
+	s->tp[stage - 1].a.lseq = s->lseq;
+	s->kp[stage - 1].a.lseq = s->lseq;
 	if (s->use_tma) {
 		const TmaParams *tp = &s->tp[stage - 1];
 		TmaParams alone;
@@ -562,6 +571,7 @@ static int launch_stage(pft_solver *s, int stage, const double *standalone_dir =
 			memset(&alone.a.pr, 0, sizeof alone.a.pr);
 			alone.a.pr.nzc = s->cfg[stage - 1].nzc; alone.a.pr.nranks = 1;
 			alone.a.standalone = 1; alone.a.standalone_cur = s->cur; alone.a.dir_standalone = *standalone_dir;
+			alone.a.dataflow = 0;
 			tp = &alone;
 		}
 		switch (stage) {
@@ -877,6 +887,22 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	}
 	CUS(cudaMalloc(&s->halo_tickets, 2 * sizeof(unsigned int)));
 	CUS(cudaMemsetAsync(s->halo_tickets, 0, 2 * sizeof(unsigned int), s->stream));
+	{
+		// data flow between stages needs one geometry for all five stages (second-generation kernels, same R) and
+		// programmatic dependent launch (without it the kernels serialise anyway)
+		bool same = s->cfg[0].ver == 2 && s->pdl && env_int("PFT_DATAFLOW", 1) != 0;
+		for (int st = 1; st < 5; st++)
+			same = same && s->cfg[st].ver == 2 && s->cfg[st].grid.x == s->cfg[0].grid.x && s->cfg[st].grid.y == s->cfg[0].grid.y &&
+			       s->cfg[st].grid.z == s->cfg[0].grid.z && s->cfg[st].zc == s->cfg[0].zc;
+		s->dataflow = same;
+		if (same) {
+			const size_t n = (size_t)s->cfg[0].grid.x * s->cfg[0].grid.y * s->cfg[0].grid.z;
+			for (int st = 0; st < 4; st++) {
+				CUS(cudaMalloc(&s->done[st], n * sizeof(unsigned long long)));
+				CUS(cudaMemsetAsync(s->done[st], 0, n * sizeof(unsigned long long), s->stream));
+			}
+		}
+	}
 
 	CUS(cudaMalloc(&s->ctl, sizeof(StepCtl)));
 	CUS(cudaMemsetAsync(s->ctl, 0, sizeof(StepCtl), s->stream));
@@ -921,6 +947,7 @@ extern "C" int pft_destroy(pft_solver *s)
 			if (s->peer_base[r] && s->peer_base[r] != s->slab) cudaIpcCloseMemHandle(s->peer_base[r]);
 	if (s->slab) cudaFree(s->slab);
 	if (s->halo_tickets) cudaFree(s->halo_tickets);
+	for (int st = 0; st < 4; st++) if (s->done[st]) cudaFree(s->done[st]);
 	if (s->stage_buf) cudaFree(s->stage_buf);
 	if (s->ctl) cudaFree(s->ctl);
 	if (s->tab_dev) cudaFree(s->tab_dev);
@@ -1320,6 +1347,7 @@ static int enqueue_attempt(pft_solver *s, int live_cur)
 	const bool nccl_mode = s->cs.nranks > 1 && !s->p2p;
 	const int outs[5] = {A_K1, A_A3, A_K3, A_K4, live_cur ? A_X : A_XN};
 	int rc;
+	s->lseq++;
 	for (int stage = 1; stage <= 5; stage++) {
 		if ((rc = launch_stage(s, stage))) return rc;
 		if (nccl_mode && (rc = exchange_pair(s, s->heat ? s->arr[outs[stage - 1]][0] : nullptr, s->arr[outs[stage - 1]][1]))) return rc;

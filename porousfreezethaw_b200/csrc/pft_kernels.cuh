@@ -120,6 +120,12 @@ struct StageArgs {
 	int fin_mode;
 	int standalone, standalone_cur;             // a single right-hand-side evaluation outside the time loop (pft_rhs_host)
 	double dir_standalone;
+	// stage-to-stage data flow (merson_stage_v2): a CTA of stage s+1 starts as soon as the CTAs of stage s it reads from
+	// are done, instead of waiting for the whole stage-s grid (see dep_wait)
+	int dataflow;
+	unsigned long long lseq;                    // number of the attempt these launches belong to, counted by the HOST
+	unsigned long long *done_mine;              // [chunk][tile_y][tile_x]: this stage's CTAs write lseq when their output is stored
+	const unsigned long long *done_prev;        // the same array of the stage before
 };
 
 // what a stage kernel reads from the control block when it starts
@@ -281,6 +287,25 @@ inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return _
 inline void st_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 #endif
 
+#ifndef PFT_CUDA_EMU
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// orders what this thread has observed through ordinary loads before its later TMA requests (asynchronous proxy)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#else
+inline unsigned long long ld_acquire_gpu(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_gpu(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline void fence_proxy_async() {}
+#endif
+
 // programmatic dependent launch (stage kernels are launched with programmatic stream serialization):
 // pdl_launch() lets the NEXT launch of the stream start filling SMs as this launch's CTAs retire -- it
 // fires once every CTA of this launch has issued it, so the successor never competes with this launch
@@ -294,13 +319,46 @@ inline void pdl_wait() {}
 inline void pdl_launch() {}
 #endif
 
-// chunk processed by this CTA: the two boundary chunks come first in launch order, so that
-// their planes reach the neighbours while the interior is still being computed
+// chunk processed by this CTA.  Launch order = zig-zag from both ends of the slab towards the middle
+// (0, nzc-1, 1, nzc-2, ...): the two boundary chunks come first, so that their planes reach the neighbouring
+// slabs while the interior is still being computed, and a chunk's z-neighbours are at most two positions away
+// in launch order, so that the CTAs the next stage starts with do not depend on the last ones of this stage
+// (stage-to-stage data flow, dep_wait).
 __device__ __forceinline__ int chunk_of_block(int nzc)
 {
 	const int z = blockIdx.z;
-	if (nzc < 3) return z;
-	return z == 0 ? nzc - 1 : (z == 1 ? 0 : z - 1);      // the top chunk pushes its plane last: give it the head start
+	return (z & 1) ? nzc - 1 - (z >> 1) : (z >> 1);
+}
+
+// ---- stage-to-stage data flow --------------------------------------------------------------------------------
+// Within an attempt every array is written by exactly one stage and read only by later ones, and a CTA reads its
+// tile plus one ring of cells and one plane below and above its chunk.  So a CTA of stage s+1 may start once the
+// 27 CTAs of stage s around its own position are done; it need not wait for the stragglers of the whole grid (on a
+// 2 M-cell slab the SMs idle 15-22 % of every stage kernel in the tail of the last wave).  Every CTA of stages 1-4
+// publishes `lseq` (the host's attempt number) in done_mine[] when its output is stored -- also when it has nothing
+// to do -- and the CTAs of stages 2-5 wait on done_prev[] instead of griddepcontrol.wait.  Stage 1 keeps the full
+// wait: it needs the step decision, which needs every CTA of stage 5.  Launch order guarantees progress: a dependent
+// grid becomes resident only when every CTA of its predecessor has started (pdl_launch at CTA entry).
+__device__ __forceinline__ long long cta_slot(int chunk) { return ((long long)chunk * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; }
+
+__device__ __forceinline__ void dep_wait(const StageArgs &a, int chunk, int nzc, int tid)
+{
+	if (tid < 27) {
+		const int X = (int)blockIdx.x + tid % 3 - 1, Y = (int)blockIdx.y + (tid / 3) % 3 - 1, Z = chunk + tid / 9 - 1;
+		if (X >= 0 && X < (int)gridDim.x && Y >= 0 && Y < (int)gridDim.y && Z >= 0 && Z < nzc) {
+			const unsigned long long *f = &a.done_prev[((long long)Z * gridDim.y + Y) * gridDim.x + X];
+			while (ld_acquire_gpu(f) < a.lseq) { }
+		}
+	}
+	__syncthreads();
+	if (tid == 0) fence_proxy_async();
+}
+
+__device__ __forceinline__ void dep_signal(const StageArgs &a, int chunk, int tid)
+{
+	if (!a.dataflow) return;
+	__syncthreads();                         // every thread's stores precede thread 0's fence (CTA barrier)
+	if (tid == 0) { __threadfence(); st_release_gpu(&a.done_mine[cta_slot(chunk)], a.lseq); }
 }
 
 __device__ __forceinline__ void halo_wait(const PeerArgs &pr, unsigned long long hseq, bool lo, bool hi, int tid)

@@ -100,10 +100,14 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 		fence_mbar_init();
 	}
 	__syncthreads();
-	pdl_wait();                                   // from here on this launch reads what its predecessor wrote
+	// from here on this launch reads what its predecessor wrote: the whole predecessor (stage 1, or data flow off),
+	// or the CTAs of the stage before that surround this one
+	const int my_chunk = chunk_of_block(a.pr.nzc);
+	if (STAGE == 1 || !a.dataflow) pdl_wait();
+	else dep_wait(a, my_chunk, a.pr.nzc, tid);
 	StageScalars sc;
-	if (!stage_begin<STAGE>(a, sc)) return;
-	if (STAGE == 1 && !a.standalone && ctl_ld(&a.ctl->skip1)) { halo_skip(a.pr, sc.hseq); return; }
+	if (!stage_begin<STAGE>(a, sc)) { if (STAGE != 5) dep_signal(a, my_chunk, tid); return; }
+	if (STAGE == 1 && !a.standalone && ctl_ld(&a.ctl->skip1)) { halo_skip(a.pr, sc.hseq); dep_signal(a, my_chunk, tid); return; }
 	const OutPtrs w = out_ptrs<STAGE>(a, sc.cur);
 	const double ha = sc.ha;
 	halo_wait(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);     // peer path: the neighbours' planes of the previous launch have landed
@@ -288,6 +292,7 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 	if (it < nplanes) { plane(std::integral_constant<int, 1>(), it); it++; }
 
 	halo_signal(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);
+	if (STAGE != 5) dep_signal(a, my_chunk, tid);
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite, smem_t, P.smem_bytes);
 }
 

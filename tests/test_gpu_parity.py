@@ -250,6 +250,30 @@ def test_fullsize_invariance(gpu_lib, hr_state, monkeypatch, env, flags):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("grid", [(200, 200, 50), (100, 100, 200), (50, 50, 100)])
+def test_stage_data_flow_matches_grid_wait(gpu_lib, monkeypatch, grid):
+    """stage s+1 starting on the CTAs of stage s around it (dep_wait, the default) against the same kernels waiting for
+    the whole predecessor grid (PFT_DATAFLOW=0), on short grids where the overlap is largest: 1500 attempts, state,
+    step counts and fields bit-identical"""
+    n1, n2, n3 = grid
+    spec = cases.cube_case(n1, nz=n3, calc_mode=1, spheres=200)
+    spec.n2 = n2
+    u, p, gl = spec.initial_fields()
+    out = []
+    for flow in ("1", "0"):
+        monkeypatch.setenv("PFT_DATAFLOW", flow)
+        sol = SlabSolver(spec, lib_path=gpu_lib)
+        sol.upload_interior(u, p, gl)
+        sol.rasterise(spec.spheres)
+        r = sol.solve(spec.final_time, max_attempts=1500)
+        out.append((r, sol.download_interior()))
+        sol.close()
+    (r1, f1), (r0, f0) = out
+    assert (r1.t, r1.h, r1.steps, r1.steps_total) == (r0.t, r0.h, r0.steps, r0.steps_total)
+    for a, b in zip(f1, f0):
+        assert np.array_equal(a, b)
+
+
 def test_fullsize_sanity(hr_state):
     spec, (u, p, gl), r, (u1, p1, gl1) = hr_state
     assert np.array_equal(gl, gl1)                      # the glass field is static (equation.c:731)
