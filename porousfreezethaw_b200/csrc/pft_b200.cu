@@ -1582,6 +1582,12 @@ extern "C" int pft_group_create_planes(const pft_case *whole, int ngpus, const i
 		if (g->planes[r] < 2 && ngpus > 1) { delete g; return fail(PFT_EINVAL, "slab %d would hold fewer than 2 planes", r); }
 	}
 	if (sum != whole->n3) { delete g; return fail(PFT_EINVAL, "the slabs hold %d planes, the block has %d", sum, whole->n3); }
+#ifndef PFT_CUDA_EMU
+	// one slab per GPU: the CTAs of a slab spin on flags that the neighbouring slab's CTAs write, which must not compete for the same SMs
+	for (int r = 0; r < ngpus; r++)
+		for (int q = 0; q < r; q++)
+			if (g->devices[q] == g->devices[r]) { int d_ = g->devices[r]; delete g; return fail(PFT_EINVAL, "device %d appears twice in the group: one slab per GPU", d_); }
+#endif
 	int rc = group_build_members(g);
 	if (rc) { delete g; return rc; }
 	*out = g;

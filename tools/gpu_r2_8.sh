@@ -1,6 +1,5 @@
 #!/bin/bash
-# round 2, 8 GPUs of one box: multi-GPU tests (in-process groups, the drop-in with PFT_NGPUS), torchrun bench at 8 and 4,
-# the single-process end-to-end figure through RK_MPI_SA_solve on all GPUs
+# round 2, 8 GPUs of one box: multi-GPU tests (in-process groups, the drop-in with PFT_NGPUS), torchrun bench at 8 and 4
 set -x
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
@@ -8,6 +7,4 @@ timeout 900 python -m pytest tests -m gpu -x -q -k "multi_gpu" > gpurun_out/pyte
 for n in 8 4; do
   EXTRA=""; [ $n -ne 8 ] && EXTRA="--also none"
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n $EXTRA > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err; echo "bench n=$n rc=$?"
-  tail -c 300 gpurun_out/bench_n$n.err
 done
-timeout 600 python bench.py --also none --no-cpu-baseline --no-parity --repeats 3 > gpurun_out/bench_n1_dropin8.json 2> gpurun_out/bench_n1_dropin8.err; echo "n1 rc=$?"
