@@ -731,7 +731,9 @@ def main():
             "data": "DRY RUN on the CPU emulation (tests only): not a measurement" if dry else "synthetic",
             "config": {"workload": spec.name, "grid": [spec.n1, spec.n2, spec.n3], "calc_mode": spec.calc_mode,
                        "geometry": info["geo"], "mode": frag["mode"], "variant": args.variant,
-                       "cache": "inputs larger than L2 (no flush needed)" if sol.cells * 13 * 8 > 2 * 126e6 else "working set fits L2",
+                       "cache": ("inputs larger than L2 (no flush needed)" if sol.cells * 13 * 8 > 2 * 126e6 else
+                                 "working set %d MB per GPU against 126 MB of L2, no flush: an attempt re-reads what the "
+                                 "previous one wrote, as in production" % (sol.cells * 13 * 8 // 1000000)),
                        "parallelism": f"z-slabs x{N}", "tile": [st["tile_x"], st["tile_y"]], "z_chunk": st["z_chunk"],
                        "rhs_evals_per_attempt": frag["rhs_evals_per_attempt"],
                        "timing": f"median of {args.repeats} regions of {attempts} attempts, each: barrier + synchronize, CUDA events on the solver stream, max over ranks",

@@ -294,6 +294,13 @@ static int choose_chunks(int tiles_xy, int n3, int sms)
 	long nzc = (target + tiles_xy / 2) / tiles_xy;
 	const long most = std::max(1, n3 / 7);
 	nzc = std::max(1L, std::min(nzc, most));
+	// small grids (50x50x100: 10 tiles): with fewer than two CTAs per SM the launch is latency-bound, and
+	// thinner chunks pay -- 4 planes per chunk measured +34% there, while 100x100x200 (1000 CTAs at 8
+	// planes) loses 4-20% when cut thinner (profiles/r02_tune2_small.txt)
+	if (tiles_xy * nzc < 2L * sms) {
+		const long want = (2L * sms + tiles_xy - 1) / tiles_xy;
+		nzc = std::max(nzc, std::min(want, (long)std::max(1, n3 / 4)));
+	}
 	return (int)nzc;
 }
 
