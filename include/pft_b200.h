@@ -128,6 +128,9 @@ typedef struct {
 	long   noop_launches;    /* stage launches that found the integration already finished (run-ahead tail) */
 	int    kernel_generation;/* of the dominant stage kernel: 0 merson_stage, 1 merson_stage_tma, 2 merson_stage_v2 */
 	int    rows_per_thread;  /* cells per thread of that kernel */
+	int    speculative_stage1; /* 1: attempts run as [S2 S3 S4 S5 S1'] -- K1 of the next attempt is evaluated from stage 5's
+	                            candidate while the step decision is still being taken (PFT_SPEC=0 turns it off) */
+	int    reserved_;
 } pft_stats;
 
 const char *pft_last_error(void);

@@ -43,7 +43,8 @@ class PftStats(C.Structure):
                 ("tile_x", C.c_int), ("tile_y", C.c_int), ("z_chunk", C.c_int), ("threads", C.c_int), ("grid_blocks", C.c_int),
                 ("bytes_per_field", C.c_long), ("host_wait_ms", C.c_double), ("host_launch_ms", C.c_double),
                 ("device_pow", C.c_int), ("runahead", C.c_int), ("noop_launches", C.c_long),
-                ("kernel_generation", C.c_int), ("rows_per_thread", C.c_int)]
+                ("kernel_generation", C.c_int), ("rows_per_thread", C.c_int),
+                ("speculative_stage1", C.c_int), ("reserved_", C.c_int)]
 
 
 # every symbol include/pft_b200.h declares

@@ -152,7 +152,8 @@ enum {
 	P_u_noise_amp, P_ball_radius
 };
 
-enum { A_X = 0, A_K1, A_A3, A_K3, A_K4, A_XN, A_COUNT };   // array pairs (u,p); order = pft_debug_fetch `which`
+enum { A_X = 0, A_K1, A_A3, A_K3, A_K4, A_XN, A_K1B, A_COUNT };   // array pairs (u,p); order = pft_debug_fetch `which`
+// (A_K1B: speculative stage 1 keeps one K1 buffer per state pair -- A_K1 goes with A_X, A_K1B with A_XN)
 
 struct StageTimer { cudaEvent_t a, b; int stage; };
 
@@ -198,6 +199,11 @@ struct pft_solver {
 	cudaEvent_t ev0, ev1;
 	bool k1_valid;
 	double k1_t;
+	// speculative stage 1 (pft_ctl.h): attempts are launched as [S2 S3 S4 S5 S1'], two control blocks alternate
+	bool spec_ok;         // the build, the kernel variant and the flags allow it
+	bool spec;            // ... and so does the transport (set by build_params)
+	bool k1_uncounted;    // K1 of the state at rest came from an S1' that no counter has seen yet (rhs_evals)
+	unsigned long long hbase;   // halo-flag sequence base at rest (mirror of StepCtl.hbase)
 	ncclComm_t comm;
 	bool have_comm;
 	bool profile;
@@ -223,7 +229,7 @@ struct pft_solver {
 	TmaParams tp[5];
 	// stage-to-stage data flow (pft_kernels.cuh, dep_wait): completion words of the CTAs of stages 1-4
 	bool dataflow;
-	unsigned long long *done[4];
+	unsigned long long *done[5];
 	unsigned long long lseq;                   // attempts enqueued so far (host count; the flags carry it)
 };
 
@@ -479,7 +485,8 @@ static void fill_peer_args(pft_solver *s, PeerArgs *pr, int stage)
 	for (int q = 0; q < R; q++) pr->ranks[q] = (SyncBlock *)s->peer_base[q];
 	for (int oi = 0; oi < 2; oi++) {
 		// stage 5 writes the candidate state pair: index [cur ^ 1], i.e. entry 0 = pair A_X, entry 1 = pair A_XN
-		const int out = (stage == 5) ? (oi == 0 ? A_X : A_XN) : outs[stage - 1];
+		// (speculative stage 1: K1 likewise has a buffer per pair, see out_ptrs)
+		const int out = (stage == 5) ? (oi == 0 ? A_X : A_XN) : (stage == 1 && s->spec && oi == 1) ? A_K1B : outs[stage - 1];
 		if (r > 0) {        // the lower neighbour's UPPER ghost plane (index n3'+1) and its halo_flag[1]
 			char *pb = s->peer_base[r - 1];
 			const size_t gp = (size_t)(s->peer_n3[r - 1] + 1) * plane_b;
@@ -501,6 +508,7 @@ static void fill_peer_args(pft_solver *s, PeerArgs *pr, int stage)
 static int build_params(pft_solver *s)
 {
 	const bool separate_nccl = s->cs.nranks > 1 && !s->p2p;
+	s->spec = s->spec_ok && !separate_nccl;
 	for (int stage = 1; stage <= 5; stage++) {
 		const StageCfg &cf = s->cfg[stage - 1];
 		KParams &kp = s->kp[stage - 1];
@@ -525,8 +533,11 @@ static int build_params(pft_solver *s)
 		a.pr.rank = s->cs.rank;
 		a.pr.nranks = s->p2p ? s->cs.nranks : 1;       // the in-kernel error-max exchange exists on the peer path only
 		a.dataflow = s->dataflow ? 1 : 0;
-		a.done_mine = (s->dataflow && stage <= 4) ? s->done[stage - 1] : nullptr;
-		a.done_prev = (s->dataflow && stage >= 2) ? s->done[stage - 2] : nullptr;
+		a.done_mine = (s->dataflow && (stage <= 4 || s->spec)) ? s->done[stage - 1] : nullptr;
+		a.done_prev = (s->dataflow && stage >= 2) ? s->done[stage - 2] : (s->spec && stage == 1) ? s->done[4] : nullptr;
+		a.spec = s->spec ? 1 : 0;
+		a.k1u2[0] = s->arr[A_K1][0]; a.k1p2[0] = s->arr[A_K1][1];
+		a.k1u2[1] = s->arr[A_K1B][0]; a.k1p2[1] = s->arr[A_K1B][1];
 		if (stage == 5) {
 			a.slot = s->slot_dev;
 			a.tab = s->tab_dev;
@@ -549,6 +560,10 @@ static int build_params(pft_solver *s)
 			if (!rc) rc = make_tensor_map(s, &tp.maps[2 * np], s->gl, cf.bx, cf.by);
 			if (!rc) rc = make_tensor_map(s, &tp.xalt[0], s->arr[A_XN][1], cf.bx, cf.by);
 			if (!rc) rc = make_tensor_map(s, &tp.xalt[1], s->arr[A_XN][0], cf.bx, cf.by);
+			if (!rc && s->spec && (stage == 2 || stage >= 4)) {
+				rc = make_tensor_map(s, &tp.k1alt[0], s->arr[A_K1B][1], cf.bx, cf.by);
+				if (!rc) rc = make_tensor_map(s, &tp.k1alt[1], s->arr[A_K1B][0], cf.bx, cf.by);
+			}
 			if (rc) return rc;
 		}
 	}
@@ -559,7 +574,7 @@ static int build_params(pft_solver *s)
 static int exchange_pair(pft_solver *s, double *u, double *p);
 
 // one stage launch.  standalone != nullptr: a single right-hand-side evaluation outside the time loop
-static int launch_stage(pft_solver *s, int stage, const double *standalone_dir = nullptr)
+static int launch_stage(pft_solver *s, int stage, const double *standalone_dir = nullptr, bool s1spec = false)
 {
 	if (!s->params_ok) { int rc_ = build_params(s); if (rc_) return rc_; }
 	StageTimer tm{};
@@ -570,6 +585,7 @@ static int launch_stage(pft_solver *s, int stage, const double *standalone_dir =
 	cudaError_t e;
 	s->tp[stage - 1].a.lseq = s->lseq;
 	s->kp[stage - 1].a.lseq = s->lseq;
+	s->tp[stage - 1].a.s1spec = s1spec ? 1 : 0;
 	if (s->use_tma) {
 		const TmaParams *tp = &s->tp[stage - 1];
 		TmaParams alone;
@@ -578,7 +594,7 @@ static int launch_stage(pft_solver *s, int stage, const double *standalone_dir =
 			memset(&alone.a.pr, 0, sizeof alone.a.pr);
 			alone.a.pr.nzc = s->cfg[stage - 1].nzc; alone.a.pr.nranks = 1;
 			alone.a.standalone = 1; alone.a.standalone_cur = s->cur; alone.a.dir_standalone = *standalone_dir;
-			alone.a.dataflow = 0;
+			alone.a.dataflow = 0; alone.a.spec = 0; alone.a.s1spec = 0;
 			tp = &alone;
 		}
 		switch (stage) {
@@ -872,6 +888,10 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	CUS(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 	CUS(cudaEventCreate(&s->ev0)); CUS(cudaEventCreate(&s->ev1));
 	const size_t fb = ((size_t)s->field * sizeof(double) + 255) & ~(size_t)255;
+	// speculative stage 1 needs the second-generation kernels with stage-to-stage data flow and the device controller
+	// (checked again below, once those are known to be on); PFT_SPEC=0 keeps the classic launch order
+	const bool want_spec = s->cfg[0].ver == 2 && s->pdl && env_int("PFT_DATAFLOW", 1) != 0 && env_int("PFT_SPEC", 1) != 0 &&
+	                       pow_gate().usable && !(flags & (PFT_FLAG_HOST_POW | PFT_FLAG_RECOMPUTE_K1));
 	{
 		// layout: identical on every rank of a run with equal slab depth; offsets are exchanged anyway
 		size_t off = (sizeof(SyncBlock) + 255) & ~(size_t)255;
@@ -880,6 +900,7 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 				// calc_mode 10/11: du/dt == 0 (equation.c:708), so u is static: no K/aux arrays for it,
 				// and the candidate state shares the one temperature array
 				if (!s->heat && q == 0 && a != A_X) { s->off[a][q] = 0; continue; }
+				if (a == A_K1B && !want_spec) { s->off[a][q] = 0; continue; }
 				s->off[a][q] = off; off += fb;
 			}
 		s->off_gl = off; off += fb;
@@ -904,16 +925,16 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 		s->dataflow = same;
 		if (same) {
 			const size_t n = (size_t)s->cfg[0].grid.x * s->cfg[0].grid.y * s->cfg[0].grid.z;
-			for (int st = 0; st < 4; st++) {
+			for (int st = 0; st < 5; st++) {
 				CUS(cudaMalloc(&s->done[st], n * sizeof(unsigned long long)));
 				CUS(cudaMemsetAsync(s->done[st], 0, n * sizeof(unsigned long long), s->stream));
 			}
 		}
 	}
 
-	CUS(cudaMalloc(&s->ctl, sizeof(StepCtl)));
-	CUS(cudaMemsetAsync(s->ctl, 0, sizeof(StepCtl), s->stream));
-	CUS(cudaHostAlloc(&s->ctl_host, sizeof(StepCtl), cudaHostAllocDefault));
+	CUS(cudaMalloc(&s->ctl, 2 * sizeof(StepCtl)));             // two blocks: speculative stage 1 alternates between them
+	CUS(cudaMemsetAsync(s->ctl, 0, 2 * sizeof(StepCtl), s->stream));
+	CUS(cudaHostAlloc(&s->ctl_host, 2 * sizeof(StepCtl), cudaHostAllocDefault));
 	CUS(cudaHostAlloc(&s->slot, sizeof(HostSlot), cudaHostAllocMapped));
 	memset(s->slot, 0, sizeof(HostSlot));
 	CUS(cudaHostGetDevicePointer(&s->slot_dev, s->slot, 0));
@@ -936,6 +957,7 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 		s->st.kernel_generation = cf.ver; s->st.rows_per_thread = cf.R;
 	}
 	s->st.bytes_per_field = (long)fb;
+	s->spec_ok = want_spec && s->dataflow && s->dev_pow;
 	s->st.device_pow = s->dev_pow ? 1 : 0;
 	s->st.runahead = s->depth;
 	*out = s;
@@ -954,7 +976,7 @@ extern "C" int pft_destroy(pft_solver *s)
 			if (s->peer_base[r] && s->peer_base[r] != s->slab) cudaIpcCloseMemHandle(s->peer_base[r]);
 	if (s->slab) cudaFree(s->slab);
 	if (s->halo_tickets) cudaFree(s->halo_tickets);
-	for (int st = 0; st < 4; st++) if (s->done[st]) cudaFree(s->done[st]);
+	for (int st = 0; st < 5; st++) if (s->done[st]) cudaFree(s->done[st]);
 	if (s->stage_buf) cudaFree(s->stage_buf);
 	if (s->ctl) cudaFree(s->ctl);
 	if (s->tab_dev) cudaFree(s->tab_dev);
@@ -1147,6 +1169,8 @@ extern "C" int pft_debug_fetch(pft_solver *s, int which, double *u, double *p)
 	int pair = which;
 	if (which == A_X) pair = s->cur ? A_XN : A_X;
 	if (which == A_XN) pair = s->cur ? A_X : A_XN;
+	if (which == A_K1B && !s->arr[A_K1B][1]) return fail(PFT_EINVAL, "bad array id %d", which);
+	if (s->spec && which == A_K1) pair = s->cur ? A_K1B : A_K1;       // K1 of the state at rest (one buffer per pair)
 	int rc;
 	if (u) {
 		if (s->arr[pair][0]) { if ((rc = dense_io(s, u, s->arr[pair][0], 1))) return rc; }
@@ -1348,13 +1372,20 @@ static int wait_seq(pft_solver *s, const volatile unsigned long long *p, unsigne
 	return 0;
 }
 
-// the launches of ONE attempt: [S1 (skipped on the device while K1 is valid), S2, S3, S4, S5 (+ the decision)]
-static int enqueue_attempt(pft_solver *s, int live_cur)
+// the launches of ONE attempt: [S1 (skipped on the device while K1 is valid), S2, S3, S4, S5 (+ the decision)];
+// with speculative stage 1: [S1 only at solve entry and only if K1 is not valid], S2, S3, S4, S5 (+ the decision), S1'
+static int enqueue_attempt(pft_solver *s, int live_cur, bool entry_s1)
 {
 	const bool nccl_mode = s->cs.nranks > 1 && !s->p2p;
 	const int outs[5] = {A_K1, A_A3, A_K3, A_K4, live_cur ? A_X : A_XN};
 	int rc;
 	s->lseq++;
+	if (s->spec) {
+		if (entry_s1 && (rc = launch_stage(s, 1))) return rc;
+		for (int stage = 2; stage <= 5; stage++)
+			if ((rc = launch_stage(s, stage))) return rc;
+		return launch_stage(s, 1, nullptr, true);
+	}
 	for (int stage = 1; stage <= 5; stage++) {
 		if ((rc = launch_stage(s, stage))) return rc;
 		if (nccl_mode && (rc = exchange_pair(s, s->heat ? s->arr[outs[stage - 1]][0] : nullptr, s->arr[outs[stage - 1]][1]))) return rc;
@@ -1388,8 +1419,10 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 	bool interrupted = false;
 
 	// ---- the control block of this call (RK_MPI_SAsolver_hybrid2.c:316-325), written by the host while the device is idle
-	StepCtl &c = *s->ctl_host;
-	memset(&c, 0, sizeof c);
+	// (speculative stage 1: the first attempt of this call is number lseq+1 and reads block (lseq+1) & 1)
+	const int blk = s->spec ? (int)((s->lseq + 1ull) & 1ull) : 0;
+	StepCtl &c = s->ctl_host[blk];
+	memset(s->ctl_host, 0, 2 * sizeof(StepCtl));
 	c.t = sys->t; c.h = sys->h;
 	c.final_time = final_time; c.h_min = sys->h_min; c.delta = sys->delta;
 	c.delta_local = sys->delta_local ? 1 : 0; c.handle_nan = sys->handle_nan ? 1 : 0;
@@ -1397,13 +1430,18 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 	c.steps = sys->steps; c.steps_total = sys->steps_total; c.rhs_evals = sys->rhs_evals;
 	c.max_attempts = sys->max_attempts;
 	c.switch_time = s->cs.param[P_phase_switch_time]; c.top_temp1 = s->cs.param[P_top_temp1]; c.top_temp2 = s->cs.param[P_top_temp2];
-	c.cur = s->cur; c.aseq = s->aseq;
+	c.cur = s->cur; c.aseq = s->aseq; c.hbase = s->hbase;
+	c.spec = s->spec ? 1 : 0;
 	c.skip1 = (s->k1_valid && s->k1_t == sys->t && !c.recompute_k1) ? 1 : 0;                      // :373
 	ctl_begin(c);
+	if (c.skip1 && s->k1_uncounted) c.rhs_evals++;         // that K1 was evaluated by the S1' that closed the previous call
+	s->k1_uncounted = false;
+	c.ready = s->lseq + 1ull; c.closed_from = ~0ull;
+	s->ctl_host[blk ^ 1].closed_from = ~0ull;
 	sys->last_nan = 0;                                                                           // :316
 	const long rhs0 = sys->rhs_evals, steps0 = sys->steps;
 
-	if (cudaMemcpyAsync(s->ctl, s->ctl_host, sizeof(StepCtl), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return fail(PFT_ECUDA, "control block upload failed");
+	if (cudaMemcpyAsync(s->ctl, s->ctl_host, 2 * sizeof(StepCtl), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return fail(PFT_ECUDA, "control block upload failed");
 	cudaEventRecord(s->ev0, s->stream);
 
 	const unsigned long long seq0 = s->aseq;
@@ -1420,7 +1458,7 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 		//      attempt -- fixed-step mode -- enqueues exactly one) to `depth`
 		const unsigned long long window = std::min<unsigned long long>((unsigned long long)depth, 1ull + (done - seq0));
 		while (enq - done < window && enq - seq0 < budget) {
-			if ((rc = enqueue_attempt(s, live_cur))) goto device_error;
+			if ((rc = enqueue_attempt(s, live_cur, enq == seq0 && !c.skip1))) goto device_error;
 			enq++;
 		}
 		if (enq == done) { rc = fail(PFT_ESTATE, "attempt budget exhausted but the device did not stop"); goto device_error; }
@@ -1476,7 +1514,8 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 		s->st.noop_launches += (long)(enq - last.seq) * 5;
 		// (stage launches that returned at once are not right-hand-side evaluations)
 		long rhs = (long)last.rhs_evals;
-		if (interrupted && last.status == ST_RUNNING) rhs -= 1;      // stage 1 of the next attempt was counted but never enqueued
+		// stage 1 of the next attempt was counted but never enqueued (with speculative stage 1 it has run: S1')
+		if (interrupted && last.status == ST_RUNNING && !s->spec) rhs -= 1;
 		s->st.rhs_evals += rhs - rhs0;
 		sys->rhs_evals = rhs;
 	}
@@ -1487,7 +1526,14 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 	sys->last_nan = last.last_nan;
 	s->cur = last.cur;
 	s->aseq = last.seq;
-	s->k1_valid = (last.seq > seq0) ? (last.accept == 0) : s->k1_valid;     // after a rejected attempt K1 == f(t, x) still holds
+	if (last.seq > seq0) s->hbase = last.hbase;
+	else s->hbase = c.hbase;                                                // (no attempt ran: the entry launch took its number)
+	if (s->spec && last.seq > seq0) {
+		// K1 of the state at rest always exists: kept after a rejected attempt, evaluated by S1' after an accepted one
+		s->k1_valid = true;
+		s->k1_uncounted = last.accept && last.status != ST_RUNNING;         // (ctl_prepare counts it only when the run goes on)
+	} else
+		s->k1_valid = (last.seq > seq0) ? (last.accept == 0) : s->k1_valid;     // after a rejected attempt K1 == f(t, x) still holds
 	s->k1_t = last.t;
 	if (interrupted) ret = PFT_SOLVE_INTERRUPTED;
 	else if (last.status == ST_BUDGET) ret = PFT_SOLVE_BUDGET;
@@ -1498,8 +1544,8 @@ device_error:
 	cudaStreamSynchronize(s->stream);
 	drain_timers(s);
 	// what the device did to the control block is unknown: bring the host's mirror back in step with it
-	if (s->slot->seq >= s->aseq) { s->aseq = s->slot->seq; s->cur = s->slot->cur; }
-	s->k1_valid = false;
+	if (s->slot->seq >= s->aseq) { s->aseq = s->slot->seq; s->cur = s->slot->cur; if (s->slot->seq > seq0) s->hbase = s->slot->hbase; else s->hbase = c.hbase; }
+	s->k1_valid = false; s->k1_uncounted = false;
 	return rc;
 }
 
@@ -1823,6 +1869,7 @@ extern "C" int pft_get_stats(pft_solver *s, pft_stats *out)
 {
 	if (!s || !out) return fail(PFT_EINVAL, "null argument");
 	*out = s->st;
+	out->speculative_stage1 = (s->params_ok ? s->spec : (s->spec_ok && !(s->cs.nranks > 1 && !s->p2p))) ? 1 : 0;
 	return 0;
 }
 

@@ -10,9 +10,17 @@
 // the outcome of the previous one: the host enqueues attempts ahead of the device and only watches
 // a progress slot (pft_b200.cu).  No host round trip, no host spin, in the time loop.
 //
+// Speculative stage 1 (StepCtl.spec, pft_b200.cu): K1 of the NEXT attempt, f(candidate state), does not depend
+// on the decision either -- only on stage 5's output -- so the launches of an attempt become
+// [S2 S3 S4 S5 S1'] with S1' writing the K1 buffer that goes with the candidate pair.  The decision then merely
+// selects which (x, K1) pair is live (StepCtl.cur), and the grid-wide wait for it moves from "before stage 1"
+// to "before stage 2", where it hides behind S1'.  Two control blocks alternate by attempt parity: the decision
+// of attempt L reads block L&1 and WRITES block (L+1)&1, so S1' of attempt L still reads a stable block.
+//
 // All arithmetic is IEEE double in the reference's order; x^0.2 comes from pft_pow.h.
 #pragma once
 #include "pft_pow.h"
+#include <stddef.h>
 
 namespace pft {
 
@@ -47,7 +55,15 @@ struct StepCtl {
 	unsigned int ticket;
 	int nonfinite;
 	double red[2];                   // {eps, nonfinite} of this slab when the decision is taken elsewhere (NCCL / host pow)
+	// ---- speculative stage 1 (two alternating blocks; see the header comment)
+	unsigned long long hbase;        // halo-flag sequence base: S1 (at solve entry, if K1 is not valid) +0, S2..S5 +1..+4, S1' +5
+	int spec, pad_;
+	// (not copied from block to block: the words the stage kernels wait on)
+	unsigned long long ready;        // host attempt number this block is valid for
+	unsigned long long closed_from;  // attempts numbered >= this lie beyond the end of the integration (~0: open)
 };
+// 8-byte words of a block that the decision carries over to the next block
+#define PFT_CTL_COPY_WORDS (offsetof(pft::StepCtl, ready) / 8)
 
 // progress slot in pinned, mapped host memory; written by the controller after every attempt
 struct HostSlot {
@@ -62,6 +78,7 @@ struct HostSlot {
 	long long steps, steps_total, attempts, rhs_evals;
 	int last_nan, delta_local;
 	double h3_attempt;               // |h/3| of the attempt (DELTA_LOCAL scaling of eps, :578)
+	unsigned long long hbase;        // StepCtl.hbase after the attempt
 };
 
 PFT_HD double ctl_dirichlet(const StepCtl &c, double t)
@@ -86,6 +103,7 @@ PFT_HD void ctl_prepare(StepCtl &c)
 PFT_HD void ctl_begin(StepCtl &c)
 {
 	c.command = 0; c.status = ST_RUNNING; c.last_nan = 0; c.attempts = 0; c.sys_h_set = 0;
+	if (!c.skip1) c.hbase += 1;      // the stage-1 launch at solve entry gets a halo sequence number of its own
 	if ((c.final_time > c.t && c.h < 0) || (c.final_time < c.t && c.h > 0)) c.h *= -1;
 	const double d = c.final_time - c.t;
 	if (c.h == 0 || (d < 0 ? -d : d) <= (c.h < 0 ? -c.h : c.h)) { c.h = d; c.command |= CMD_FINISHED; }
@@ -124,7 +142,7 @@ PFT_HD int ctl_decide(StepCtl &c, double eps, int nonfinite, const PowTables *ta
 	if (command & CMD_NAN) {                                       // :626-646
 		c.last_nan = 1;
 		c.skip1 = c.recompute_k1 ? 0 : 1;
-		if (command & CMD_h_TOO_SMALL) { c.status = ST_NAN; c.skip1 = 1; c.aseq++; return result; }
+		if (command & CMD_h_TOO_SMALL) { c.status = ST_NAN; c.skip1 = 1; c.aseq++; c.hbase += 5; return result; }
 		c.h = h / 10;
 		c.command = 0;
 	} else {
@@ -151,6 +169,7 @@ PFT_HD int ctl_decide(StepCtl &c, double eps, int nonfinite, const PowTables *ta
 		c.status = ST_BUDGET;
 	}
 	c.aseq++;
+	c.hbase += 5;
 	if (c.status == ST_RUNNING) ctl_prepare(c);
 	return result;
 }
@@ -166,6 +185,7 @@ PFT_HD void ctl_publish(const StepCtl &c, HostSlot *s, double eps, int nonfinite
 	s->sys_h = c.sys_h; s->sys_h_set = c.sys_h_set; s->cur = c.cur;
 	s->steps = c.steps; s->steps_total = c.steps_total; s->attempts = c.attempts; s->rhs_evals = c.rhs_evals;
 	s->last_nan = c.last_nan;
+	s->hbase = c.hbase;
 }
 
 }  // namespace pft

@@ -126,6 +126,11 @@ struct StageArgs {
 	unsigned long long lseq;                    // number of the attempt these launches belong to, counted by the HOST
 	unsigned long long *done_mine;              // [chunk][tile_y][tile_x]: this stage's CTAs write lseq when their output is stored
 	const unsigned long long *done_prev;        // the same array of the stage before
+	// speculative stage 1 (pft_ctl.h): `ctl` points at two blocks, the attempt reads block lseq & 1; K1 has two
+	// buffers that go with the two state pairs
+	int spec;
+	int s1spec;                                 // this stage-1 launch is S1' (evaluates the candidate of attempt lseq)
+	double *k1u2[2], *k1p2[2];
 };
 
 // what a stage kernel reads from the control block when it starts
@@ -141,17 +146,26 @@ template <class T> __device__ __forceinline__ T ctl_ld(const T *p) { return __ld
 template <class T> inline T ctl_ld(const T *p) { return *p; }
 #endif
 
+// the control block an attempt's launches read
+__device__ __forceinline__ StepCtl *ctl_block(const StageArgs &a) { return a.ctl + (a.spec ? (int)(a.lseq & 1ull) : 0); }
+
 template <int STAGE>
 __device__ __forceinline__ bool stage_begin(const StageArgs &a, StageScalars &sc)
 {
 	if (a.standalone) { sc.ha = sc.hb = 0.0; sc.dir_u = a.dir_standalone; sc.cur = a.standalone_cur; sc.hseq = 0; return true; }
 	// (L2 loads: the block was written by the previous attempt's controller thread while CTAs of this
 	//  launch may already have been resident on the SM -- programmatic dependent launch)
-	const StepCtl *c = a.ctl;
+	const StepCtl *c = ctl_block(a);
 	if (ctl_ld(&c->status) != ST_RUNNING) return false;   // enqueued beyond the end of the integration: nothing to do
 	sc.cur = ctl_ld(&c->cur);
-	sc.dir_u = ctl_ld(&c->dir[STAGE - 1]);
-	sc.hseq = 5ull * ctl_ld(&c->aseq) + STAGE;
+	if (a.spec) {
+		// launch order of an attempt: [S1 at solve entry] S2 S3 S4 S5 S1'
+		sc.hseq = ctl_ld(&c->hbase) + (STAGE == 1 ? (a.s1spec ? 5 : 0) : STAGE - 1);
+		sc.dir_u = ctl_ld(&c->dir[(STAGE == 1 && a.s1spec) ? 4 : STAGE - 1]);     // S1' evaluates at t + h
+	} else {
+		sc.dir_u = ctl_ld(&c->dir[STAGE - 1]);
+		sc.hseq = 5ull * ctl_ld(&c->aseq) + STAGE;
+	}
 	sc.ha = sc.hb = 0.0;
 	if (STAGE == 2) { sc.ha = ctl_ld(&c->h3); sc.hb = ctl_ld(&c->h6); }
 	if (STAGE == 4) sc.ha = ctl_ld(&c->h8);
@@ -358,7 +372,27 @@ __device__ __forceinline__ void dep_signal(const StageArgs &a, int chunk, int ti
 {
 	if (!a.dataflow) return;
 	__syncthreads();                         // every thread's stores precede thread 0's fence (CTA barrier)
-	if (tid == 0) { __threadfence(); st_release_gpu(&a.done_mine[cta_slot(chunk)], a.lseq); }
+	// (S1' produces K1 for the attempt that follows: stage 2 of attempt lseq+1 waits for it)
+	if (tid == 0) { __threadfence(); st_release_gpu(&a.done_mine[cta_slot(chunk)], a.lseq + (a.s1spec ? 1ull : 0ull)); }
+}
+
+// speculative stage 1: the block of attempt lseq becomes valid when the decision of attempt lseq-1 is published
+// (or the host wrote it at solve entry).  Returns false when the launch lies beyond the end of the integration.
+// Only stage 2 ever waits here for real: it is the first launch of an attempt that needs the decision.
+__device__ __forceinline__ bool ctl_wait(const StageArgs &a, int tid)
+{
+	__shared__ int s_go;
+	if (tid == 0) {
+		const StepCtl *b = ctl_block(a);
+		int go;
+		for (;;) {
+			if (ld_acquire_gpu(&b->ready) == a.lseq) { go = 1; break; }
+			if (ld_acquire_gpu(&b->closed_from) <= a.lseq) { go = 0; break; }
+		}
+		s_go = go;
+	}
+	__syncthreads();
+	return s_go != 0;
 }
 
 __device__ __forceinline__ void halo_wait(const PeerArgs &pr, unsigned long long hseq, bool lo, bool hi, int tid)
@@ -409,9 +443,11 @@ template <int STAGE>
 __device__ __forceinline__ OutPtrs out_ptrs(const StageArgs &a, int cur)
 {
 	OutPtrs o;
-	const int oi = (STAGE == 5) ? (cur ^ 1) : 0;
-	o.ou = (STAGE == 5) ? a.xu[oi] : a.ou;
-	o.op = (STAGE == 5) ? a.xp[oi] : a.op;
+	// stage 5 writes the candidate pair; with speculative stage 1 K1 has a buffer per state pair: S1' fills the one
+	// of the candidate pair, the stage 1 at solve entry the one of the live pair
+	const int oi = (STAGE == 5) ? (cur ^ 1) : (STAGE == 1 && a.spec) ? (a.s1spec ? cur ^ 1 : cur) : 0;
+	o.ou = (STAGE == 5) ? a.xu[oi] : (STAGE == 1 && a.spec) ? a.k1u2[oi] : a.ou;
+	o.op = (STAGE == 5) ? a.xp[oi] : (STAGE == 1 && a.spec) ? a.k1p2[oi] : a.op;
 	o.lo_u = a.pr.lo_u[oi]; o.lo_p = a.pr.lo_p[oi];
 	o.hi_u = a.pr.hi_u[oi]; o.hi_p = a.pr.hi_p[oi];
 	return o;
@@ -440,6 +476,18 @@ __device__ __forceinline__ void store_out(const OutPtrs &w, long long o, long lo
 // dependent accesses to the control block and to the pow tables; staged in shared memory by the whole CTA
 // (two coalesced copies) it costs ~2 us instead of ~10 us of serial global-memory latency -- which is 5 % of an
 // attempt on the thin slabs of an 8-GPU run.
+// speculative stage 1: hand the freshly written block to attempt lseq+1; at the end of the integration close both
+// blocks for every later attempt (launches enqueued ahead return at once)
+__device__ __forceinline__ void ctl_release_next(StepCtl *cur_blk, StepCtl *nxt, unsigned long long lseq, int status)
+{
+	__threadfence();
+	if (status != ST_RUNNING) {
+		*(volatile unsigned long long *)&nxt->closed_from = lseq + 1ull;
+		st_release_gpu(&cur_blk->closed_from, lseq + 1ull);
+	}
+	st_release_gpu(&nxt->ready, lseq + 1ull);
+}
+
 __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, double emax, int nonfinite, void *scratch, unsigned scratch_bytes)
 {
 	// CTA max through a shared-memory atomic on the bit pattern (non-negative doubles order
@@ -451,7 +499,8 @@ __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, doubl
 	if (emax > 0.0) atomicMax(&s_bits, (unsigned long long)__double_as_longlong(emax));
 	if (nonfinite) atomicOr(&s_nonfinite, 1);
 	__syncthreads();
-	StepCtl *ctl = a.ctl;
+	StepCtl *ctl = ctl_block(a);             // the block this attempt read
+	StepCtl *nxt = a.spec ? a.ctl + (int)((a.lseq + 1ull) & 1ull) : ctl;      // the block the next attempt reads
 	if (tid == 0) {
 		if (s_bits) atomicMax(&ctl->eps_bits, s_bits);
 		if (s_nonfinite) atomicOr(&ctl->nonfinite, 1);
@@ -512,9 +561,10 @@ __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, doubl
 			ctl_publish(c, a.slot, eps, s_nonfinite, cmd, h_attempt);
 		}
 		__syncthreads();
-		for (unsigned i = tid; i < sizeof(StepCtl) / 8; i += nthr) ((unsigned long long *)ctl)[i] = sc_ctl[i];
+		for (unsigned i = tid; i < PFT_CTL_COPY_WORDS; i += nthr) ((unsigned long long *)nxt)[i] = sc_ctl[i];
 		__syncthreads();
 		if (tid == 0) {
+			if (a.spec) ctl_release_next(ctl, nxt, a.lseq, ((const StepCtl *)sc_ctl)->status);
 			__threadfence_system();
 			*(volatile unsigned long long *)&a.slot->seq = seq;
 		}
@@ -534,9 +584,11 @@ __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, doubl
 			*(volatile unsigned long long *)&s->seq_eps = seq;
 		} else {
 			const double h_attempt = ctl->h;
-			const int cmd = ctl_decide(*ctl, eps, nfl, a.tab, 0.0);
+			if (a.spec) for (unsigned i = 0; i < PFT_CTL_COPY_WORDS; i++) ((unsigned long long *)nxt)[i] = ((const unsigned long long *)ctl)[i];
+			const int cmd = ctl_decide(*nxt, eps, nfl, a.tab, 0.0);
 			__threadfence();
-			ctl_publish(*ctl, s, eps, nfl, cmd, h_attempt);
+			ctl_publish(*nxt, s, eps, nfl, cmd, h_attempt);
+			if (a.spec) ctl_release_next(ctl, nxt, a.lseq, nxt->status);
 			__threadfence_system();
 			*(volatile unsigned long long *)&s->seq = seq;
 		}

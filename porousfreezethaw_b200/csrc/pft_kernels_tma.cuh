@@ -38,6 +38,7 @@ constexpr int TMA_STAGES = 3;
 struct alignas(64) TmaParams {
 	CUtensorMap maps[TMA_MAX_ARRAYS];   // order: p-type arrays, u-type arrays, gl (see stage_np); x = pair A_X
 	CUtensorMap xalt[2];                 // the other state pair (A_XN): p, u -- used when StepCtl.cur == 1
+	CUtensorMap k1alt[2];                // speculative stage 1: the K1 buffer that goes with pair A_XN: p, u
 	Consts c;
 	Geom g;
 	StageArgs a;

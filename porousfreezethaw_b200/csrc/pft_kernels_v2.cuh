@@ -103,11 +103,16 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 	// from here on this launch reads what its predecessor wrote: the whole predecessor (stage 1, or data flow off),
 	// or the CTAs of the stage before that surround this one
 	const int my_chunk = chunk_of_block(a.pr.nzc);
-	if (STAGE == 1 || !a.dataflow) pdl_wait();
-	else dep_wait(a, my_chunk, a.pr.nzc, tid);
+	const bool s1spec = (STAGE == 1) && a.s1spec;       // S1': K1 of the next attempt from stage 5's candidate (pft_ctl.h)
+	const bool signals = (STAGE != 5) || a.spec;        // stage 5 has a successor within the attempt only then
+	if ((STAGE == 1 && !s1spec) || !a.dataflow || a.standalone) pdl_wait();
+	else {
+		if (a.spec && !ctl_wait(a, tid)) { if (signals) dep_signal(a, my_chunk, tid); return; }
+		dep_wait(a, my_chunk, a.pr.nzc, tid);
+	}
 	StageScalars sc;
-	if (!stage_begin<STAGE>(a, sc)) { if (STAGE != 5) dep_signal(a, my_chunk, tid); return; }
-	if (STAGE == 1 && !a.standalone && ctl_ld(&a.ctl->skip1)) { halo_skip(a.pr, sc.hseq); dep_signal(a, my_chunk, tid); return; }
+	if (!stage_begin<STAGE>(a, sc)) { if (signals) dep_signal(a, my_chunk, tid); return; }
+	if (STAGE == 1 && !a.standalone && !s1spec && ctl_ld(&ctl_block(a)->skip1)) { halo_skip(a.pr, sc.hseq); dep_signal(a, my_chunk, tid); return; }
 	const OutPtrs w = out_ptrs<STAGE>(a, sc.cur);
 	const double ha = sc.ha;
 	halo_wait(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);     // peer path: the neighbours' planes of the previous launch have landed
@@ -115,7 +120,9 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 	// plane q goes to raw buffer q % 3: one tensor copy per array.  The state pair x is array 0 (p) and
 	// array IU (u) of every stage but the third; which pair holds x is StepCtl.cur.
 	const uint32_t plane_bytes = (uint32_t)(NA * BX * (RY + 2) * sizeof(double));
-	const bool alt = (STAGE != 3) && sc.cur != 0;
+	// (S1' reads the candidate pair; with speculative stage 1 K1 -- array 1 of stages 2, 4, 5 -- has a buffer per pair)
+	const bool alt = (STAGE != 3) && (sc.cur ^ (s1spec ? 1 : 0)) != 0;
+	const bool altk = (STAGE == 2 || STAGE == 4 || STAGE == 5) && a.spec && sc.cur != 0;
 	auto issue = [&](int q, int b) {
 		mbar_arrive_expect_tx(&full[b], plane_bytes);
 		#pragma unroll
@@ -123,6 +130,8 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 			const CUtensorMap *map = &P.maps[m];
 			if (alt && m == 0) map = &P.xalt[0];
 			if (alt && m == IU) map = &P.xalt[1];
+			if (NP > 1 && altk && m == 1) map = &P.k1alt[0];
+			if (NP > 1 && altk && m == IU + 1) map = &P.k1alt[1];
 			tma_load_3d(raw + b * RS + m * AS, map, i0 - 2, j0 - 1, k0 + q, &full[b]);
 		}
 	};
@@ -292,7 +301,7 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 	if (it < nplanes) { plane(std::integral_constant<int, 1>(), it); it++; }
 
 	halo_signal(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);
-	if (STAGE != 5) dep_signal(a, my_chunk, tid);
+	if (signals) dep_signal(a, my_chunk, tid);
 	if (STAGE == 5) stage5_finish(a, tid, emax, nonfinite, smem_t, P.smem_bytes);
 }
 

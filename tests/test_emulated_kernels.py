@@ -61,3 +61,54 @@ def test_second_generation_kernel_variants(emu_lib, monkeypatch, rows, nobar):
     st = sol.stats()
     sol.close()
     assert st["kernel_generation"] == 2 and st["rows_per_thread"] == int(rows[-1])
+
+
+def test_speculative_stage1_matches_classic_order(emu_lib, monkeypatch):
+    """Attempts launched as [S2 S3 S4 S5 S1'] with two alternating control blocks and one K1 buffer per state pair
+    (the default) against the classic [S1 .. S5] order (PFT_SPEC=0): several solve calls, attempt budgets that end a
+    call after a rejected and after an accepted attempt, an upload in between (K1 invalid: stage 1 runs at solve
+    entry) -- step sequence, counters (rhs_evals included) and fields bit-identical."""
+    import numpy as np
+    from porousfreezethaw_b200.solver import SlabSolver
+    monkeypatch.setenv("PFT_TX", "8")
+    monkeypatch.setenv("PFT_TY", "4")
+    monkeypatch.setenv("PFT_ZCHUNKS", "3")
+    spec = cases.small_case(13, 7, 11, calc_mode=1)
+    u, p, gl = spec.initial_fields()
+    runs = []
+    for on in ("1", "0"):
+        monkeypatch.setenv("PFT_SPEC", on)
+        sol = SlabSolver(spec, lib_path=emu_lib)
+        sol.upload_interior(u, p, gl)
+        sol.rasterise(spec.spheres)
+        trace = []
+        for budget in (1, 2, 1, 3, 5, 4):
+            r = sol.solve(6.0, max_attempts=budget)
+            trace.append((r.code, r.t, r.h, r.steps, r.steps_total, r.rhs_evals))
+        k1 = sol.debug_fetch(1)
+        if on == "1":
+            # K1 of the state at rest is what stage 1 computes from it (S1' ran on stage 5's candidate)
+            x = np.zeros(3 * sol.SIZE)
+            sol.download(x)
+            probe = SlabSolver(spec, lib_path=emu_lib)
+            probe.upload_interior(u, p, gl)
+            probe.rasterise(spec.spheres)
+            xx = np.zeros(3 * sol.SIZE)
+            probe.download(xx)
+            xx[:2 * sol.SIZE] = x[:2 * sol.SIZE]
+            dw = probe.rhs_host(r.t, xx).reshape(3, sol.N3, sol.N2, sol.N1)[:, 2:-2, 2:-2, 2:-2]
+            probe.close()
+            assert np.array_equal(dw[0], k1[0]) and np.array_equal(dw[1], k1[1])
+        uu, pp, gg = sol.download_interior()
+        sol.upload_interior(uu, pp, None)             # same values, but K1 is no longer known to be valid
+        r = sol.solve(6.0)
+        trace.append((r.code, r.t, r.h, r.steps, r.steps_total, r.rhs_evals))
+        st = sol.stats()
+        assert st["speculative_stage1"] == int(on)
+        runs.append((trace, k1, sol.download_interior()))
+        sol.close()
+    (t1, _, f1), (t0, _, f0) = runs
+    assert t1 == t0
+    assert t1[-1][0] == 0 and t1[-1][1] == 6.0
+    for a, b in zip(f1, f0):
+        assert np.array_equal(a, b)

@@ -252,26 +252,33 @@ def test_fullsize_invariance(gpu_lib, hr_state, monkeypatch, env, flags):
 
 @pytest.mark.parametrize("grid", [(200, 200, 50), (100, 100, 200), (50, 50, 100)])
 def test_stage_data_flow_matches_grid_wait(gpu_lib, monkeypatch, grid):
-    """stage s+1 starting on the CTAs of stage s around it (dep_wait, the default) against the same kernels waiting for
-    the whole predecessor grid (PFT_DATAFLOW=0), on short grids where the overlap is largest: 1500 attempts, state,
-    step counts and fields bit-identical"""
+    """The three ways an attempt's launches are ordered on the device, on short grids where the overlap is largest:
+    (default) [S2 S3 S4 S5 S1'] with K1 of the next attempt evaluated speculatively from stage 5's candidate and
+    stage s+1 starting on the CTAs of stage s around it (dep_wait); the classic [S1 .. S5] with that data flow
+    (PFT_SPEC=0); and the same kernels waiting for the whole predecessor grid (PFT_DATAFLOW=0).  1500 attempts in
+    three solve calls: state, step counts, rhs_evals and fields bit-identical."""
     n1, n2, n3 = grid
     spec = cases.cube_case(n1, nz=n3, calc_mode=1, spheres=200)
     spec.n2 = n2
     u, p, gl = spec.initial_fields()
     out = []
-    for flow in ("1", "0"):
+    for flow, spc in (("1", "1"), ("1", "0"), ("0", "0")):
         monkeypatch.setenv("PFT_DATAFLOW", flow)
+        monkeypatch.setenv("PFT_SPEC", spc)
         sol = SlabSolver(spec, lib_path=gpu_lib)
+        assert sol.stats()["speculative_stage1"] == int(spc)
         sol.upload_interior(u, p, gl)
         sol.rasterise(spec.spheres)
-        r = sol.solve(spec.final_time, max_attempts=1500)
-        out.append((r, sol.download_interior()))
+        trace = []
+        for budget in (7, 993, 500):
+            r = sol.solve(spec.final_time, max_attempts=budget)
+            trace.append((r.t, r.h, r.steps, r.steps_total, r.rhs_evals))
+        out.append((trace, sol.download_interior()))
         sol.close()
-    (r1, f1), (r0, f0) = out
-    assert (r1.t, r1.h, r1.steps, r1.steps_total) == (r0.t, r0.h, r0.steps, r0.steps_total)
-    for a, b in zip(f1, f0):
-        assert np.array_equal(a, b)
+    for trace, fields in out[1:]:
+        assert trace == out[0][0]
+        for a, b in zip(fields, out[0][1]):
+            assert np.array_equal(a, b)
 
 
 def test_fullsize_sanity(hr_state):
