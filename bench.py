@@ -737,7 +737,9 @@ def main():
                        "parallelism": f"z-slabs x{N}", "tile": [st["tile_x"], st["tile_y"]], "z_chunk": st["z_chunk"],
                        "rhs_evals_per_attempt": frag["rhs_evals_per_attempt"],
                        "timing": f"median of {args.repeats} regions of {attempts} attempts, each: barrier + synchronize, CUDA events on the solver stream, max over ranks",
-                       "controller": "device (twin of the host libm pow), attempts enqueued ahead: %d" % st["runahead"] if st["device_pow"] else "host pow per attempt"},
+                       "controller": "device (twin of the host libm pow), attempts enqueued ahead: %d" % st["runahead"] if st["device_pow"] else "host pow per attempt",
+                       "launch_order": "S2 S3 S4 S5 S1' (K1 of the next attempt evaluated speculatively from stage 5's candidate)"
+                                       if st.get("speculative_stage1") else "S1 S2 S3 S4 S5"},
             "e2e": e2e, "gpu_launches": info["launches"], "clocks": clocks, "roofline": roofline,
             "device_ms_regions": frag["device_ms_regions"],
             "wall_ms_per_step": frag["wall_ms_per_step"],

@@ -210,7 +210,7 @@ struct pft_solver {
 	bool pdl;             // stage kernels use programmatic dependent launch (off while profiling stages)
 	std::vector<StageTimer> timers;
 	pft_stats st;
-	// one device slab: [SyncBlock][13 field arrays]; peers map it (CUDA IPC between processes, peer access inside one)
+	// one device slab: [SyncBlock][15 field arrays (13 without speculative stage 1)]; peers map it (CUDA IPC between processes, peer access inside one)
 	char *slab;
 	size_t slab_bytes;
 	size_t off[A_COUNT][2], off_gl;            // byte offsets of the arrays inside the slab (same on every rank)
