@@ -1453,10 +1453,14 @@ extern "C" int pft_solve(pft_solver *s, pft_system *sys, double final_time)
 	memset(&last, 0, sizeof last);
 	double t_mark = host_ms();
 
+	// a call whose first step already reaches final_time (fixed-step mode: :324 set CMD_FINISHED) most likely needs ONE
+	// attempt: its window opens up from one.  Any other call starts with the full window -- launches beyond the end
+	// return at once, and the device never waits for the host while the window opens.
+	// (PFT_SLOW_OPEN=1: every call opens its window from one -- for A/B measurements)
+	const unsigned long long open0 = ((c.command & CMD_FINISHED) || env_int("PFT_SLOW_OPEN", 0)) ? 1ull : (unsigned long long)depth;
 	while (status == ST_RUNNING) {
-		// ---- keep the launch queue filled: the window opens up from one attempt (a solve call that needs a single
-		//      attempt -- fixed-step mode -- enqueues exactly one) to `depth`
-		const unsigned long long window = std::min<unsigned long long>((unsigned long long)depth, 1ull + (done - seq0));
+		// ---- keep the launch queue filled
+		const unsigned long long window = std::min<unsigned long long>((unsigned long long)depth, open0 + (done - seq0));
 		while (enq - done < window && enq - seq0 < budget) {
 			if ((rc = enqueue_attempt(s, live_cur, enq == seq0 && !c.skip1))) goto device_error;
 			enq++;
