@@ -66,17 +66,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// The wait carries a suspend-time hint: a warp whose plane has not landed sleeps in hardware (NANOSLEEP.SYNCS)
+// instead of re-issuing try_wait.  In the barrier-free stages 1 and 3 a warp that runs ahead of its CTA waits at
+// almost every plane (SYNCS + BRA were ~12 % of the instructions in ncu's source view); measured, the hint is
+// neutral (61.2-61.3 Gcell-RHS/s either way, profiles/r02_mbar_hint_ab.txt) -- those spins sat in idle issue slots.
+#ifndef PFT_MBAR_SUSPEND_NS
+#define PFT_MBAR_SUSPEND_NS 1000000u
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	asm volatile(
 		"{\n"
 		".reg .pred p;\n"
 		"PFT_MBAR_WAIT:\n"
+#ifdef PFT_MBAR_NO_HINT
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#else
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+#endif
 		"@p bra PFT_MBAR_DONE;\n"
 		"bra PFT_MBAR_WAIT;\n"
 		"PFT_MBAR_DONE:\n"
-		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(PFT_MBAR_SUSPEND_NS) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
 {
