@@ -60,6 +60,28 @@ def test_group_variants(emu_lib, flags):
     _run(cases.small_case(12, 10, 16, calc_mode=1), 2, emu_lib, T=8.0, flags=flags)
 
 
+@pytest.mark.parametrize("env", [{"PFT_SPEC": "0"}, {"PFT_DATAFLOW": "0"}])
+def test_group_classic_launch_order(emu_lib, monkeypatch, env):
+    """the peer-memory protocol in the classic order S1..S5 (halo sequence 5*aseq + stage, stage 1 skipped after a
+    rejected attempt) -- the default is the speculative order S2..S5 S1', which every other test of this file runs"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = GroupSolver(cases.small_case(12, 10, 16, calc_mode=1), 2, lib_path=emu_lib)
+    assert g.member_stats(0)["speculative_stage1"] == 0
+    g.close()
+    r = _run(cases.small_case(12, 10, 19, calc_mode=1), 3, emu_lib, T=10.0, service=True)
+    assert r.steps_total > r.steps
+    _run(cases.small_case(12, 10, 16, calc_mode=0), 2, emu_lib, T=400.0, chunks=3, budget=7)
+
+
+def test_group_speculative_order_is_default(emu_lib):
+    g = GroupSolver(cases.small_case(12, 10, 16, calc_mode=1), 3, lib_path=emu_lib)
+    try:
+        assert all(g.member_stats(r)["speculative_stage1"] == 1 for r in range(3))
+    finally:
+        g.close()
+
+
 def test_group_budget_resume(emu_lib):
     _run(cases.small_case(12, 10, 16, calc_mode=0), 2, emu_lib, T=400.0, chunks=3, budget=7)
 
