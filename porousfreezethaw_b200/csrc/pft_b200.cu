@@ -202,6 +202,7 @@ struct pft_solver {
 	// speculative stage 1 (pft_ctl.h): attempts are launched as [S2 S3 S4 S5 S1'], two control blocks alternate
 	bool spec_ok;         // the build, the kernel variant and the flags allow it
 	bool spec;            // ... and so does the transport (set by build_params)
+	bool spec_earlyout;   // S1' CTAs that start after a rejecting decision return at once (PFT_SPEC_EARLYOUT=0: A/B)
 	bool k1_uncounted;    // K1 of the state at rest came from an S1' that no counter has seen yet (rhs_evals)
 	unsigned long long hbase;   // halo-flag sequence base at rest (mirror of StepCtl.hbase)
 	ncclComm_t comm;
@@ -585,7 +586,7 @@ static int launch_stage(pft_solver *s, int stage, const double *standalone_dir =
 	cudaError_t e;
 	s->tp[stage - 1].a.lseq = s->lseq;
 	s->kp[stage - 1].a.lseq = s->lseq;
-	s->tp[stage - 1].a.s1spec = s1spec ? 1 : 0;
+	s->tp[stage - 1].a.s1spec = s1spec ? (s->spec_earlyout ? 1 : 2) : 0;
 	if (s->use_tma) {
 		const TmaParams *tp = &s->tp[stage - 1];
 		TmaParams alone;
@@ -958,6 +959,7 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 	}
 	s->st.bytes_per_field = (long)fb;
 	s->spec_ok = want_spec && s->dataflow && s->dev_pow;
+	s->spec_earlyout = env_int("PFT_SPEC_EARLYOUT", 1) != 0;
 	s->st.device_pow = s->dev_pow ? 1 : 0;
 	s->st.runahead = s->depth;
 	*out = s;

@@ -129,7 +129,8 @@ struct StageArgs {
 	// speculative stage 1 (pft_ctl.h): `ctl` points at two blocks, the attempt reads block lseq & 1; K1 has two
 	// buffers that go with the two state pairs
 	int spec;
-	int s1spec;                                 // this stage-1 launch is S1' (evaluates the candidate of attempt lseq)
+	int s1spec;                                 // this stage-1 launch is S1' (evaluates the candidate of attempt lseq);
+	                                            // 2: ... and does not look whether the decision has overtaken it (A/B)
 	double *k1u2[2], *k1p2[2];
 };
 
@@ -593,6 +594,19 @@ __device__ __forceinline__ void stage5_finish(const StageArgs &a, int tid, doubl
 			*(volatile unsigned long long *)&s->seq = seq;
 		}
 	}
+}
+
+// S1' only: has the decision of this attempt been published already, and did it keep the old state (rejected
+// attempt, or the NaN branch)?  Then nobody will read the K1 this launch is about to evaluate.
+__device__ __forceinline__ bool candidate_rejected(const StageArgs &a, int cur, int tid)
+{
+	__shared__ int s_rej;
+	if (tid == 0) {
+		const StepCtl *nx = a.ctl + (int)((a.lseq + 1ull) & 1ull);
+		s_rej = (ld_acquire_gpu(&nx->ready) == a.lseq + 1ull && ctl_ld(&nx->cur) == cur) ? 1 : 0;
+	}
+	__syncthreads();
+	return s_rej != 0;
 }
 
 // the decision as a kernel of its own (one thread): after an NCCL all-reduce of StepCtl.red, and/or with

@@ -113,6 +113,13 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 	StageScalars sc;
 	if (!stage_begin<STAGE>(a, sc)) { if (signals) dep_signal(a, my_chunk, tid); return; }
 	if (STAGE == 1 && !a.standalone && !s1spec && ctl_ld(&ctl_block(a)->skip1)) { halo_skip(a.pr, sc.hseq); dep_signal(a, my_chunk, tid); return; }
+	if (STAGE == 1 && a.s1spec == 1 && candidate_rejected(a, sc.cur, tid)) {
+		// the decision overtook this CTA and turned the candidate down: its K1 will never be read.  (Early CTAs of S1'
+		// run before the decision exists and evaluate in vain: a rejected attempt costs part of an S1', not all of it.)
+		halo_signal(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);
+		dep_signal(a, my_chunk, tid);
+		return;
+	}
 	const OutPtrs w = out_ptrs<STAGE>(a, sc.cur);
 	const double ha = sc.ha;
 	halo_wait(a.pr, sc.hseq, chunk_lo, chunk_hi, tid);     // peer path: the neighbours' planes of the previous launch have landed
