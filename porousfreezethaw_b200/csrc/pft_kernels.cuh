@@ -356,15 +356,18 @@ __device__ __forceinline__ int chunk_of_block(int nzc)
 // grid becomes resident only when every CTA of its predecessor has started (pdl_launch at CTA entry).
 __device__ __forceinline__ long long cta_slot(int chunk) { return ((long long)chunk * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; }
 
+__device__ __forceinline__ void dep_poll(const StageArgs &a, int chunk, int nzc, int n)
+{
+	const int X = (int)blockIdx.x + n % 3 - 1, Y = (int)blockIdx.y + (n / 3) % 3 - 1, Z = chunk + n / 9 - 1;
+	if (X >= 0 && X < (int)gridDim.x && Y >= 0 && Y < (int)gridDim.y && Z >= 0 && Z < nzc) {
+		const unsigned long long *f = &a.done_prev[((long long)Z * gridDim.y + Y) * gridDim.x + X];
+		while (ld_acquire_gpu(f) < a.lseq) { }
+	}
+}
+
 __device__ __forceinline__ void dep_wait(const StageArgs &a, int chunk, int nzc, int tid)
 {
-	if (tid < 27) {
-		const int X = (int)blockIdx.x + tid % 3 - 1, Y = (int)blockIdx.y + (tid / 3) % 3 - 1, Z = chunk + tid / 9 - 1;
-		if (X >= 0 && X < (int)gridDim.x && Y >= 0 && Y < (int)gridDim.y && Z >= 0 && Z < nzc) {
-			const unsigned long long *f = &a.done_prev[((long long)Z * gridDim.y + Y) * gridDim.x + X];
-			while (ld_acquire_gpu(f) < a.lseq) { }
-		}
-	}
+	if (tid < 27) dep_poll(a, chunk, nzc, tid);
 	__syncthreads();
 	if (tid == 0) fence_proxy_async();
 }
@@ -380,9 +383,14 @@ __device__ __forceinline__ void dep_signal(const StageArgs &a, int chunk, int ti
 // speculative stage 1: the block of attempt lseq becomes valid when the decision of attempt lseq-1 is published
 // (or the host wrote it at solve entry).  Returns false when the launch lies beyond the end of the integration.
 // Only stage 2 ever waits here for real: it is the first launch of an attempt that needs the decision.
-__device__ __forceinline__ bool ctl_wait(const StageArgs &a, int tid)
+// The wait on the block (thread 0) and the 27 polls of dep_wait (second warp) run side by side and end in ONE CTA
+// barrier: a CTA starts its first tensor load two L2 round trips after it became resident (the block's `ready`
+// word next to the completion words, then the block's scalars), which is what a stage costs on a grid of a few
+// hundred CTAs.
+__device__ __forceinline__ bool ctl_dep_wait(const StageArgs &a, int chunk, int nzc, int tid)
 {
 	__shared__ int s_go;
+	const int base = (blockDim.x * blockDim.y >= 64) ? 32 : 0;      // (tiles of fewer than 64 threads: one after the other)
 	if (tid == 0) {
 		const StepCtl *b = ctl_block(a);
 		int go;
@@ -392,7 +400,9 @@ __device__ __forceinline__ bool ctl_wait(const StageArgs &a, int tid)
 		}
 		s_go = go;
 	}
+	if (tid >= base && tid < base + 27) dep_poll(a, chunk, nzc, tid - base);
 	__syncthreads();
+	if (tid == 0) fence_proxy_async();
 	return s_go != 0;
 }
 

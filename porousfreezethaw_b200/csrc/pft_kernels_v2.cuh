@@ -107,8 +107,8 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 	const bool signals = (STAGE != 5) || a.spec;        // stage 5 has a successor within the attempt only then
 	if ((STAGE == 1 && !s1spec) || !a.dataflow || a.standalone) pdl_wait();
 	else {
-		if (a.spec && !ctl_wait(a, tid)) { if (signals) dep_signal(a, my_chunk, tid); return; }
-		dep_wait(a, my_chunk, a.pr.nzc, tid);
+		if (!a.spec) dep_wait(a, my_chunk, a.pr.nzc, tid);
+		else if (!ctl_dep_wait(a, my_chunk, a.pr.nzc, tid)) { if (signals) dep_signal(a, my_chunk, tid); return; }
 	}
 	StageScalars sc;
 	if (!stage_begin<STAGE>(a, sc)) { if (signals) dep_signal(a, my_chunk, tid); return; }
