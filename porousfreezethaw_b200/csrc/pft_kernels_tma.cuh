@@ -89,6 +89,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 		"PFT_MBAR_DONE:\n"
 		"}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(PFT_MBAR_SUSPEND_NS) : "memory");
 }
+// descriptor fetch ahead of the first tensor load (the maps live in the kernel's parameter block)
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
+{
+	asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
 {
 	asm volatile(
@@ -113,6 +118,7 @@ inline void mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	while ((uint32_t)(*bar & 1u) == parity) pft_emu::yield();
 }
+inline void tma_prefetch_desc(const CUtensorMap *) {}
 inline void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
 {
 	uint32_t n = pft_emu::tensor_load_3d(dst, map, x, y, z);

@@ -99,6 +99,10 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 		for (int b = 0; b < TMA_STAGES; b++) { mbar_init(&full[b], 1); left[b] = 0u; }
 		fence_mbar_init();
 	}
+	// the tensor-map descriptors are fetched while this CTA waits for its predecessors (warp 2: warps 0 and 1 poll)
+	if (tid >= 64 && tid < 64 + NA) tma_prefetch_desc(&P.maps[tid - 64]);
+	if (STAGE != 3 && tid >= 64 + NA && tid < 64 + NA + 2) tma_prefetch_desc(&P.xalt[tid - 64 - NA]);
+	if (NP > 1 && a.spec && tid >= 64 + NA + 2 && tid < 64 + NA + 4) tma_prefetch_desc(&P.k1alt[tid - 64 - NA - 2]);
 	__syncthreads();
 	// from here on this launch reads what its predecessor wrote: the whole predecessor (stage 1, or data flow off),
 	// or the CTAs of the stage before that surround this one
