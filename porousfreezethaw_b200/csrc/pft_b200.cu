@@ -221,6 +221,7 @@ struct pft_solver {
 	char *peer_base[PFT_MAX_RANKS];            // every rank's slab in this process' address space
 	int peer_n3[PFT_MAX_RANKS];
 	unsigned int *halo_tickets;
+	unsigned long long *halo_published;
 	pft_group *group;                          // member of an in-process group (pft_group_*)
 	// TMA path (heat modes): one tensor map per array, box = tile + halo ring
 	bool use_tma;
@@ -482,6 +483,7 @@ static void fill_peer_args(pft_solver *s, PeerArgs *pr, int stage)
 	pr->nzc = s->cfg[stage - 1].nzc;
 	pr->my_flags = ((SyncBlock *)s->slab)->halo_flag;
 	pr->tickets = s->halo_tickets;
+	pr->published = s->halo_published;
 	pr->wait_lo = (r > 0); pr->wait_hi = (r < R - 1);
 	for (int q = 0; q < R; q++) pr->ranks[q] = (SyncBlock *)s->peer_base[q];
 	for (int oi = 0; oi < 2; oi++) {
@@ -914,8 +916,10 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 		s->gl = (double *)(s->slab + s->off_gl);
 		if (!s->heat) { s->arr[A_XN][0] = s->arr[A_X][0]; s->off[A_XN][0] = s->off[A_X][0]; }
 	}
-	CUS(cudaMalloc(&s->halo_tickets, 2 * sizeof(unsigned int)));
-	CUS(cudaMemsetAsync(s->halo_tickets, 0, 2 * sizeof(unsigned int), s->stream));
+	CUS(cudaMalloc(&s->halo_tickets, 16 * sizeof(unsigned int)));
+	CUS(cudaMemsetAsync(s->halo_tickets, 0, 16 * sizeof(unsigned int), s->stream));
+	CUS(cudaMalloc(&s->halo_published, 2 * sizeof(unsigned long long)));
+	CUS(cudaMemsetAsync(s->halo_published, 0, 2 * sizeof(unsigned long long), s->stream));
 	{
 		// data flow between stages needs one geometry for all five stages (second-generation kernels, same R) and
 		// programmatic dependent launch (without it the kernels serialise anyway)
@@ -978,6 +982,7 @@ extern "C" int pft_destroy(pft_solver *s)
 			if (s->peer_base[r] && s->peer_base[r] != s->slab) cudaIpcCloseMemHandle(s->peer_base[r]);
 	if (s->slab) cudaFree(s->slab);
 	if (s->halo_tickets) cudaFree(s->halo_tickets);
+	if (s->halo_published) cudaFree(s->halo_published);
 	for (int st = 0; st < 5; st++) if (s->done[st]) cudaFree(s->done[st]);
 	if (s->stage_buf) cudaFree(s->stage_buf);
 	if (s->ctl) cudaFree(s->ctl);

@@ -89,7 +89,8 @@ struct PeerArgs {
 	double *hi_u[2], *hi_p[2];           // upper neighbour's lower ghost plane
 	unsigned long long *lo_flag, *hi_flag;   // the neighbours' halo_flag entries this rank signals
 	const unsigned long long *my_flags;  // this rank's halo_flag[2]
-	unsigned int *tickets;               // finished boundary CTAs, [lower, upper]
+	unsigned int *tickets;               // finished boundary CTAs, [launch sequence & 7][lower, upper]
+	unsigned long long *published;       // [lower, upper]: launch sequence of the last flag this rank sent that way
 	SyncBlock *ranks[PFT_MAX_RANKS];     // stage 5: every rank's sync block (error-max broadcast)
 	int rank, nranks;
 	int wait_lo, wait_hi;                // this slab has a lower / an upper neighbour
@@ -417,6 +418,15 @@ __device__ __forceinline__ void halo_wait(const PeerArgs &pr, unsigned long long
 	__syncthreads();
 }
 
+// one thread: the flag of launch hseq goes to a neighbour once the flag of launch hseq-1 has gone
+__device__ __forceinline__ void halo_publish(const PeerArgs &pr, int side, unsigned long long *flag, unsigned long long hseq)
+{
+	while (ld_acquire_gpu(&pr.published[side]) + 1 < hseq) { }
+	__threadfence_system();
+	st_release_sys(flag, hseq);
+	st_release_gpu(&pr.published[side], hseq);
+}
+
 __device__ __forceinline__ void halo_signal(const PeerArgs &pr, unsigned long long hseq, bool lo, bool hi, int tid)
 {
 	const bool wl = lo && pr.wait_lo, wh = hi && pr.wait_hi;
@@ -429,8 +439,14 @@ __device__ __forceinline__ void halo_signal(const PeerArgs &pr, unsigned long lo
 		// when the boundary CTAs of a launch finish together (measured, profiles/round1_tuning.md).
 		__threadfence();
 		const unsigned int n = gridDim.x * gridDim.y;
-		if (wl && atomicAdd(&pr.tickets[0], 1u) == n - 1) { pr.tickets[0] = 0u; __threadfence_system(); st_release_sys(pr.lo_flag, hseq); }
-		if (wh && atomicAdd(&pr.tickets[1], 1u) == n - 1) { pr.tickets[1] = 0u; __threadfence_system(); st_release_sys(pr.hi_flag, hseq); }
+		// With the stage-to-stage data flow a boundary CTA of launch n+1 may finish while one of launch n is still
+		// running (certainly so when an S1' CTA returns at once, candidate_rejected).  So (a) every launch counts on a
+		// ticket pair of its own, eight in rotation -- launches eight apart lie on different sides of a step decision,
+		// which needs every CTA of the attempt before it -- and (b) flags go out in launch order: a neighbour reads
+		// "flag >= n" as "the boundary planes of every launch up to n have landed".
+		unsigned int *tk = pr.tickets + 2 * (int)(hseq & 7ull);
+		if (wl && atomicAdd(&tk[0], 1u) == n - 1) { tk[0] = 0u; halo_publish(pr, 0, pr.lo_flag, hseq); }
+		if (wh && atomicAdd(&tk[1], 1u) == n - 1) { tk[1] = 0u; halo_publish(pr, 1, pr.hi_flag, hseq); }
 	}
 }
 
@@ -439,8 +455,8 @@ __device__ __forceinline__ void halo_skip(const PeerArgs &pr, unsigned long long
 {
 	if (hseq == 0) return;
 	if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0) {
-		if (pr.wait_lo) st_release_sys(pr.lo_flag, hseq);
-		if (pr.wait_hi) st_release_sys(pr.hi_flag, hseq);
+		if (pr.wait_lo) halo_publish(pr, 0, pr.lo_flag, hseq);
+		if (pr.wait_hi) halo_publish(pr, 1, pr.hi_flag, hseq);
 	}
 }
 
