@@ -352,8 +352,10 @@ __device__ __forceinline__ int chunk_of_block(int nzc)
 // 27 CTAs of stage s around its own position are done; it need not wait for the stragglers of the whole grid (on a
 // 2 M-cell slab the SMs idle 15-22 % of every stage kernel in the tail of the last wave).  Every CTA of stages 1-4
 // publishes `lseq` (the host's attempt number) in done_mine[] when its output is stored -- also when it has nothing
-// to do -- and the CTAs of stages 2-5 wait on done_prev[] instead of griddepcontrol.wait.  Stage 1 keeps the full
-// wait: it needs the step decision, which needs every CTA of stage 5.  Launch order guarantees progress: a dependent
+// to do -- and the CTAs of stages 2-5 wait on done_prev[] instead of griddepcontrol.wait.  In the classic launch
+// order stage 1 keeps the full wait: it needs the step decision, which needs every CTA of stage 5.  With speculative
+// stage 1 (pft_ctl.h) stage 5 publishes too, S1' follows it through the same 27-neighbour rule, and the one grid-wide
+// wait of an attempt is stage 2's wait for the decision (ctl_dep_wait).  Launch order guarantees progress: a dependent
 // grid becomes resident only when every CTA of its predecessor has started (pdl_launch at CTA entry).
 __device__ __forceinline__ long long cta_slot(int chunk) { return ((long long)chunk * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; }
 
