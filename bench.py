@@ -558,7 +558,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=7, help="timed regions of --steps attempts each; the median is reported")
     ap.add_argument("--workload", default=os.environ.get("PFT_BENCH_WORKLOAD", "400-SigmaP1-P-smallsigma"))
     ap.add_argument("--also", default=os.environ.get("PFT_BENCH_ALSO", "default"),
-                    help="comma-separated secondary workloads reported under `also` ('none' to skip); default: the PhysRevE-2025 200 case and "
+                    help="comma-separated secondary workloads reported under `also` ('none' to skip); default: the 100 case (one GPU only), the PhysRevE-2025 200 case and "
                          "the SURVEY 8(d)-5 weak-scaling slab 800x800x(100 N) in fixed-step mode")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -693,7 +693,9 @@ def main():
 
     # ---- secondary workloads -------------------------------------------------------------
     also = []
-    names = [] if args.also in ("none", "") else (["2025-200-GradP", "cube-800w"] if args.also == "default" else args.also.split(","))
+    # default: the PhysRevE-2025 "200" case and the weak-scaling slab at every N; the 250 k-cell "100" case (the reference's
+    # CPU-runnable configuration) on one GPU only -- there is nothing to learn from 12 planes per GPU
+    names = [] if args.also in ("none", "") else ((["100-GradP"] if N == 1 else []) + ["2025-200-GradP", "cube-800w"] if args.also == "default" else args.also.split(","))
     if dry:
         names = []
     for nm in names:
