@@ -446,8 +446,11 @@ static cudaError_t launch_v2_shape(pft_solver *s, const TmaParams &kp)
 {
 	const StageCfg &cf = s->cfg[STAGE - 1];
 	constexpr bool CAN_NOBAR = (STAGE == 1 || STAGE == 3);
+	// forming stages with the split (arrive / wait) barrier exist for the default geometry only: fixed shape, one row per thread
+	constexpr bool CAN_SPLIT = !CAN_NOBAR && R == 1;
 	if (cf.fixed) {
 		if (CAN_NOBAR && cf.nobar) return launch_v2_t<STAGE, MODEL, R, PFT_FIXED_TX, PFT_FIXED_TY, CAN_NOBAR>(s, kp);
+		if (CAN_SPLIT && cf.nobar) return launch_v2_t<STAGE, MODEL, R, PFT_FIXED_TX, PFT_FIXED_TY, CAN_SPLIT>(s, kp);
 		return launch_v2_t<STAGE, MODEL, R, PFT_FIXED_TX, PFT_FIXED_TY, false>(s, kp);
 	}
 	if (CAN_NOBAR && cf.nobar) return launch_v2_t<STAGE, MODEL, R, 0, 0, CAN_NOBAR>(s, kp);
@@ -844,7 +847,10 @@ extern "C" int pft_create(const pft_case *cs, int device, unsigned flags, pft_so
 			cf.ver = kver;
 			cf.R = 1;
 			if (kver == 2 && nrows > 0) cf.R = std::max(1, std::min(2, (int)(rows[std::min(st, nrows - 1)] - '0')));
-			cf.nobar = kver == 2 && want_nobar && (st == 0 || st == 2);
+			// stages 1, 3: barrier-free plane loop (default); stages 2, 4, 5: split barrier (PFT_SPLITBAR=1, fixed shape and R == 1 only)
+			// (PFT_SPLITBAR = 1: all three; 2 | 4 | 5: that stage only)
+			const int sb = env_int("PFT_SPLITBAR", 0);
+			cf.nobar = kver == 2 && ((st == 0 || st == 2) ? want_nobar : (sb == 1 || sb == st + 1));
 			int max_threads = env_int("PFT_THREADS", 256);     // two or three CTAs per SM overlap each other's barrier waits
 			if (max_threads < 32) max_threads = 32;
 			if (max_threads > 512) max_threads = 512;

@@ -32,7 +32,8 @@ template <int STAGE, int MODEL, int R, int CTX, int CTY, bool NOBAR>
 __global__ void __launch_bounds__(CTX > 0 ? ((CTX * CTY + 31) & ~31) : 256, (STAGE == 5 || R > 1) ? 2 : 3)
 merson_stage_v2(const __grid_constant__ TmaParams P)
 {
-	static_assert(!NOBAR || STAGE == 1 || STAGE == 3, "only the stages that read raw planes can drop the CTA barrier");
+	// NOBAR: stages 1 and 3 (they read raw planes only) run without any CTA barrier in the plane loop; the forming stages
+	// 2, 4, 5 replace their per-plane CTA barrier by an arrive / wait pair (SPLIT below)
 	const Consts &c = P.c;
 	const Geom &g = P.g;
 	const StageArgs &a = P.a;
@@ -42,6 +43,8 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 	constexpr int NP = stage_np(STAGE);
 	constexpr int NA = 2 * NP + 1;
 	constexpr bool FORM = !(STAGE == 1 || STAGE == 3);
+	constexpr bool SPLIT = FORM && NOBAR;        // forming stage with the split barrier
+	constexpr bool FREE = !FORM && NOBAR;        // barrier-free raw-plane stage
 	constexpr int IU = NP, IG = 2 * NP;          // first u-type array, the gl array
 
 	const int TX = CTX > 0 ? CTX : P.tx, TY = CTX > 0 ? CTY : P.ty;   // threads; the tile is TX x (TY*R) cells
@@ -60,6 +63,8 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 	double *tile = raw + TMA_STAGES * RS;                            // [3][2][AS]  (FORM)
 	__shared__ uint64_t full[TMA_STAGES];     // raw plane landed (TMA complete_tx)
 	__shared__ unsigned int left[TMA_STAGES]; // NOBAR: warps that have left the plane in this buffer
+	__shared__ uint64_t formed;               // split barrier of the forming stages: every warp has written its part of a state tile
+	__shared__ unsigned int formed_tick;      // ... and the ticket that elects the last of them (it requests the next raw plane)
 
 	const int i0 = blockIdx.x * TX, j0 = blockIdx.y * RY;
 	const int i = i0 + tx, jb = j0 + ty * R;                         // this thread's column, its lowest row
@@ -97,6 +102,7 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 
 	if (tid == 0) {
 		for (int b = 0; b < TMA_STAGES; b++) { mbar_init(&full[b], 1); left[b] = 0u; }
+		mbar_init(&formed, nwarps); formed_tick = 0u;
 		fence_mbar_init();
 	}
 	// the tensor-map descriptors are fetched while this CTA waits for its predecessors (warp 2: warps 0 and 1 poll)
@@ -164,7 +170,26 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 		}
 	};
 
-	uint32_t full_bits = 0;                      // parity of the next completion to wait for, per buffer
+	// Forming stages (2, 4, 5) with NOBAR: the CTA barrier at the end of every plane becomes an arrive / wait pair.
+	// A warp ARRIVES when its part of the state tile of plane k+1 is written (and with that it has finished plane k-1),
+	// computes plane k, and WAITS at the top of the next plane until every warp has arrived -- warps drift up to one plane
+	// apart instead of meeting after each.  The last warp to arrive requests raw plane q+2 into the buffer of plane q-1
+	// (every warp is past it).  Three state tiles: the tile a warp overwrites was last read two planes ago, and the wait
+	// it has just passed says that every warp has finished that plane.
+	constexpr bool split = SPLIT;
+	auto arrive_formed = [&](int q_req, int b, bool refill) {
+		__syncwarp();
+		if (lane == 0) {
+			__threadfence_block();
+			if (atomicAdd(&formed_tick, 1u) == nwarps - 1) {
+				formed_tick = 0u;
+				if (refill) issue(q_req, b);
+			}
+			mbar_arrive(&formed);
+		}
+	};
+
+	uint32_t full_bits = 0;                      // parity of the next completion to wait for, per buffer (bit 3: `formed`)
 	// register window: slot (q % 3) holds plane q -- the three roles (k-1, k, k+1) rotate with the unrolled
 	// bodies, nothing is copied.  (u and g of plane k-1 are dead once its z-face flux is kept in fz.)
 	double Pw[3][R], Uw[3][R], Gw[3][R];
@@ -201,7 +226,7 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 				um[r] = form_state<STAGE>(raw, AS, csr[r], IU, ha);
 				gm[r] = raw[IG * AS + csr[r]];
 			}
-			if (NOBAR) leave(0, 0);
+			if (FREE) leave(0, 0);
 		}
 		mbar_wait(&full[1], 0); full_bits ^= 2u;
 		const double *rb = raw + RS;
@@ -217,7 +242,8 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 		}
 		if (FORM && hduty) { t1[hs] = form_state<STAGE>(rb, AS, hs, 0, ha); t1[AS + hs] = form_state<STAGE>(rb, AS, hs, IU, ha); }
 	}
-	if (!NOBAR) __syncthreads();
+	if (split) arrive_formed(0, 0, false);
+	else if (!FREE) __syncthreads();
 
 	// one plane; J = it % 3 fixes every buffer, tile and window index at compile time
 	auto plane = [&](auto Jc, int it) {
@@ -234,6 +260,8 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 
 		// ---- request plane q+2 into the buffer plane q-1 just vacated
 		if (!NOBAR && tid == 0 && next_q <= qhi && next_q <= q + 2) { issue(next_q, bf); next_q++; }
+		// ---- split barrier: the state tile of plane k is complete, and nobody reads the tile of plane k-2 any more
+		if (split) { mbar_wait(&formed, (full_bits >> 3) & 1u); full_bits ^= 8u; }
 
 		// ---- plane k+1: form the stage input (centres -> registers, centres + ring -> its state tile)
 		if (q + 1 <= qhi) {
@@ -253,6 +281,8 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 			#pragma unroll
 			for (int r = 0; r < R; r++) { un[r] = sc.dir_u; pn[r] = pc[r]; gn[r] = gc[r]; }     // equation.c:175-183 / :251-261
 		}
+
+		if (split) arrive_formed(it + 3, bf, it >= qlo && it + 3 <= qhi);
 
 		// ---- plane k: in-plane neighbours of the column of R cells
 		const double *tp = FORM ? tile + bq * 2 * AS : rb;
@@ -296,8 +326,8 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 		}
 
 		// ---- this plane is done: raw[bq] may be refilled, its state tile overwritten (three planes later)
-		if (NOBAR) leave(q, bq);
-		else __syncthreads();
+		if (FREE) leave(q, bq);
+		else if (!split) __syncthreads();
 	};
 
 	const int nplanes = k1 - k0;

@@ -107,9 +107,13 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 				if (fibers[i].state == DONE) alive--;
 				else waiting++;
 			}
-			// CUDA requires every non-exited thread of the CTA to reach the barrier
-			for (int i = 0; i < nt; i++) if (fibers[i].state == WAITING) fibers[i].state = READY;
+			// __syncthreads: the fibers at the barrier are released once EVERY live fiber of the CTA has arrived; fibers that
+			// merely yielded (a spin on an mbarrier, a warp barrier, a flag of another device) keep running until they do
 			(void)waiting;
+			int at_barrier = 0;
+			for (int i = 0; i < nt; i++) if (fibers[i].state == WAITING) at_barrier++;
+			if (at_barrier == alive)
+				for (int i = 0; i < nt; i++) if (fibers[i].state == WAITING) fibers[i].state = READY;
 		}
 	}
 	cur = -1;

@@ -112,3 +112,21 @@ def test_speculative_stage1_matches_classic_order(emu_lib, monkeypatch):
     assert t1[-1][0] == 0 and t1[-1][1] == 6.0
     for a, b in zip(f1, f0):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_split_barrier_variant_of_forming_stages(emu_lib, monkeypatch, mode):
+    """PFT_SPLITBAR=1: stages 2, 4, 5 with an arrive / wait pair instead of the per-plane CTA barrier (warps drift up to
+    one plane apart, the last warp to arrive requests the next raw plane).  Exists for the default 50x5 tile only, so
+    the grid here is two such tiles, three z-chunks with remainder planes: fused stages and an adaptive run against
+    the oracle, bit for bit (tolerance of the oracle comparison for mode 2 as everywhere)."""
+    from porousfreezethaw_b200.solver import SlabSolver
+    monkeypatch.setenv("PFT_SPLITBAR", "1")
+    monkeypatch.setenv("PFT_ZCHUNKS", "3")
+    spec = cases.small_case(50, 10, 11, calc_mode=mode)
+    sol = SlabSolver(spec, lib_path=emu_lib)
+    st = sol.stats()
+    sol.close()
+    assert (st["tile_x"], st["tile_y"], st["kernel_generation"]) == (50, 5, 2)
+    parity.check_fused_stages(spec, emu_lib)
+    parity.check_adaptive(spec, emu_lib, T=4.0, chunks=2)
