@@ -176,6 +176,9 @@ merson_stage_v2(const __grid_constant__ TmaParams P)
 	// apart instead of meeting after each.  The last warp to arrive requests raw plane q+2 into the buffer of plane q-1
 	// (every warp is past it).  Three state tiles: the tile a warp overwrites was last read two planes ago, and the wait
 	// it has just passed says that every warp has finished that plane.
+	// Measured on B200 (profiles/r02_splitbar_ab.txt): bit-exact, but SLOWER than the CTA barrier (56.0 against 61.8
+	// Gcell-RHS/s, each forming stage +42 us) -- the warp barrier, ticket, arrive and wait per plane and warp cost more
+	// issue slots than the barrier stalls they remove.  Opt-in (PFT_SPLITBAR=1), kept as the record of that experiment.
 	constexpr bool split = SPLIT;
 	auto arrive_formed = [&](int q_req, int b, bool refill) {
 		__syncwarp();
